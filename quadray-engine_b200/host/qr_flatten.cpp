@@ -1,0 +1,402 @@
+/*
+ * qr_flatten.cpp -- engine pointer graph -> index-based scene blob.
+ *
+ * Field-by-field this follows SURVEY.md appendix B (what render0 reads):
+ *   rt_SIMD_INFOX     core/tracer/tracer.h:150-216
+ *   rt_SIMD_CONTEXT   tracer.h:426-665   (level-0 inputs, engine.cpp:3588-3596)
+ *   rt_SIMD_CAMERA    tracer.h:677-755   (engine.cpp:3559-3584)
+ *   rt_SIMD_LIGHT     tracer.h:765-811   (object.cpp:590-670)
+ *   rt_SIMD_SURFACE   tracer.h:821-969   (object.cpp:712-759, 2472-2503)
+ *   rt_SIMD_MATERIAL  tracer.h:979-1078  (object.cpp:4094-4151)
+ *   rt_ELEM           tracer.h:127-141   (encodings: engine.cpp:1120-1132,
+ *                                         1681-1695, 1845-1865, 3201-3208)
+ * The byte-offset tricks of the macro assembler (a_map/a_sgn/t_map hold
+ * offsets of SIMD fields, object.cpp:2489-2497, 4099-4100) are turned back
+ * into small indices here.
+ */
+
+#include <string.h>
+
+#include "tracer.h"
+#include "format.h"
+#include "engine.h"
+
+#include "qr_flatten.h"
+
+#define QR_FIELD (RT_SIMD_QUADS * 16)   /* bytes of one SIMD field */
+
+int32_t qr_Flattener::list_head(const rt_ELEM *head, ListKind kind)
+{
+    if (head == RT_NULL)
+    {
+        return QR_NIL;
+    }
+
+    std::unordered_map<const void *, int32_t>::iterator it =
+                                                        elem_idx.find(head);
+    if (it != elem_idx.end())
+    {
+        return it->second;
+    }
+
+    /* index the whole chain consecutively, stop at a shared tail */
+    int32_t first = (int32_t)elem_src.size();
+    for (const rt_ELEM *e = head; e != RT_NULL; e = e->next)
+    {
+        if (elem_idx.find(e) != elem_idx.end())
+        {
+            break;
+        }
+        elem_idx[e] = (int32_t)elem_src.size();
+        elem_src.push_back(e);
+        elem_kind.push_back(kind);
+    }
+    return first;
+}
+
+int32_t qr_Flattener::surface(const rt_SIMD_SURFACE *s)
+{
+    if (s == RT_NULL)
+    {
+        return QR_NIL;
+    }
+    std::unordered_map<const void *, int32_t>::iterator it = surf_idx.find(s);
+    if (it != surf_idx.end())
+    {
+        return it->second;
+    }
+    int32_t idx = (int32_t)surf_src.size();
+    surf_idx[s] = idx;
+    surf_src.push_back(s);
+    return idx;
+}
+
+int32_t qr_Flattener::material(const rt_SIMD_MATERIAL *m)
+{
+    if (m == RT_NULL)
+    {
+        return QR_NIL;
+    }
+    std::unordered_map<const void *, int32_t>::iterator it = mat_idx.find(m);
+    if (it != mat_idx.end())
+    {
+        return it->second;
+    }
+
+    qr_material r;
+    memset(&r, 0, sizeof(r));
+    r.xscal = m->xscal[0];
+    r.yscal = m->yscal[0];
+    r.xoffs = m->xoffs[0];
+    r.yoffs = m->yoffs[0];
+    r.xmask = (uint32_t)m->xmask[0];
+    r.ymask = (uint32_t)m->ymask[0];
+    r.yshft = (uint32_t)m->yshft[0];
+    r.t_map[0] = m->t_map[0] / QR_FIELD;
+    r.t_map[1] = m->t_map[1] / QR_FIELD;
+    r.l_dff = m->l_dff[0];
+    r.l_spc = m->l_spc[0];
+    r.l_pow = m->l_pow[0];
+    r.c_rfl = m->c_rfl[0];
+    r.c_trn = m->c_trn[0];
+    r.c_rfr = m->c_rfr[0];
+    r.rfr_2 = m->rfr_2[0];
+    r.c_rcp = m->c_rcp[0];
+    r.ext_2 = m->ext_2[0];
+    r.clamp = m->clamp[0];
+    r.cmask = (uint32_t)m->cmask[0];
+
+    /* texture: (xmask+1) x (ymask+1) texels of 0x00RRGGBB, power of two
+     * (object.cpp:4113-4129); a plain colour is a 1x1 texture */
+    const rt_ui32 *tex = (const rt_ui32 *)m->tex_p[0];
+    if (tex == RT_NULL)
+    {
+        throw rt_Exception("null texture pointer in qr_Flattener");
+    }
+    std::unordered_map<const void *, int32_t>::iterator tt = tex_idx.find(tex);
+    if (tt != tex_idx.end())
+    {
+        r.tex = tt->second;
+    }
+    else
+    {
+        size_t n = (size_t)(r.xmask + 1) * (size_t)(r.ymask + 1);
+        r.tex = (int32_t)texels.size();
+        tex_idx[tex] = r.tex;
+        texels.insert(texels.end(), tex, tex + n);
+    }
+
+    int32_t idx = (int32_t)mats.size();
+    mat_idx[m] = idx;
+    mats.push_back(r);
+    return idx;
+}
+
+int32_t qr_Flattener::light(const rt_SIMD_LIGHT *l)
+{
+    if (l == RT_NULL)
+    {
+        return QR_NIL;
+    }
+    std::unordered_map<const void *, int32_t>::iterator it = lgt_idx.find(l);
+    if (it != lgt_idx.end())
+    {
+        return it->second;
+    }
+
+    qr_light r;
+    memset(&r, 0, sizeof(r));
+    r.t_max  = l->t_max[0];
+    r.pos[0] = l->pos_x[0];
+    r.pos[1] = l->pos_y[0];
+    r.pos[2] = l->pos_z[0];
+    r.col[0] = l->col_r[0];
+    r.col[1] = l->col_g[0];
+    r.col[2] = l->col_b[0];
+    r.a_qdr  = l->a_qdr[0];
+    r.a_lnr  = l->a_lnr[0];
+    r.a_cnt  = l->a_cnt[0];
+
+    int32_t idx = (int32_t)lgts.size();
+    lgt_idx[l] = idx;
+    lgts.push_back(r);
+    return idx;
+}
+
+/*
+ * Resolve everything reachable from the lists and surfaces queued so far.
+ */
+void qr_Flattener::drain()
+{
+    size_t elem_done = elems.size();
+
+    while (elem_done < elem_src.size() || surf_done < surf_src.size())
+    {
+        for (; elem_done < elem_src.size(); elem_done++)
+        {
+            const rt_ELEM *e = elem_src[elem_done];
+            ListKind kind = elem_kind[elem_done];
+            qr_elem r;
+            r.data_i = 0;
+            r.data_p = QR_NIL;
+            r.simd   = QR_NIL;
+            r.next   = QR_NIL;
+
+            if (kind == LIST_SURF)
+            {
+                const rt_SIMD_SURFACE *s = (const rt_SIMD_SURFACE *)e->simd;
+                r.simd   = surface(s);
+                r.data_i = (int32_t)(e->data & 3);
+                const rt_ELEM *last = (const rt_ELEM *)(e->data & ~(rt_cell)3);
+                if (last != RT_NULL && s != RT_NULL
+                &&  (r.data_i == 1 || s->srf_t[3] < 0))
+                {
+                    r.data_p = list_head(last, LIST_SURF);
+                }
+            }
+            else
+            if (kind == LIST_LIGHT)
+            {
+                r.simd   = light((const rt_SIMD_LIGHT *)e->simd);
+                r.data_p = list_head((const rt_ELEM *)e->data, LIST_SURF);
+            }
+            else
+            {
+                const rt_SIMD_SURFACE *s = (const rt_SIMD_SURFACE *)e->simd;
+                r.simd = surface(s);
+                if (s != RT_NULL && s->srf_t[3] < 0)
+                {
+                    r.data_p = list_head((const rt_ELEM *)e->data, LIST_CLIP);
+                }
+                else
+                {
+                    r.data_i = (int32_t)e->data;
+                }
+            }
+
+            elems.push_back(r);
+        }
+
+        for (; surf_done < surf_src.size(); surf_done++)
+        {
+            const rt_SIMD_SURFACE *s = surf_src[surf_done];
+            qr_surface r;
+            memset(&r, 0, sizeof(r));
+
+            r.pos[0] = s->pos_x[0]; r.pos[1] = s->pos_y[0]; r.pos[2] = s->pos_z[0];
+            r.min[0] = s->min_x[0]; r.min[1] = s->min_y[0]; r.min[2] = s->min_z[0];
+            r.max[0] = s->max_x[0]; r.max[1] = s->max_y[0]; r.max[2] = s->max_z[0];
+            r.d_eps  = s->d_eps[0];
+            r.t_eps  = s->t_eps[0];
+            r.minmax_t = 0;
+            for (int a = 0; a < 3; a++)
+            {
+                r.minmax_t |= (s->min_t[a] != 0 ? 1 : 0) << a;
+                r.minmax_t |= (s->max_t[a] != 0 ? 1 : 0) << (3 + a);
+            }
+            r.tci[0] = s->tci_x[0]; r.tci[1] = s->tci_y[0]; r.tci[2] = s->tci_z[0];
+            r.tcj[0] = s->tcj_x[0]; r.tcj[1] = s->tcj_y[0]; r.tcj[2] = s->tcj_z[0];
+            r.tck[0] = s->tck_x[0]; r.tck[1] = s->tck_y[0]; r.tck[2] = s->tck_z[0];
+            r.sci[0] = s->sci_x[0]; r.sci[1] = s->sci_y[0]; r.sci[2] = s->sci_z[0];
+            r.sci[3] = s->sci_w[0];
+            r.scj[0] = s->scj_x[0]; r.scj[1] = s->scj_y[0]; r.scj[2] = s->scj_z[0];
+            r.c_def  = (uint32_t)s->c_def[0];
+
+            /* byte offsets of SIMD fields -> indices, object.cpp:2489-2497 */
+            r.a_map[RT_I] = s->a_map[RT_I] / QR_FIELD;
+            r.a_map[RT_J] = s->a_map[RT_J] / QR_FIELD;
+            r.a_map[RT_K] = s->a_map[RT_K] / QR_FIELD;
+            r.a_map[RT_L] = s->a_map[RT_L];
+            r.a_sgn[RT_I] = s->a_sgn[RT_I] / QR_FIELD;
+            r.a_sgn[RT_J] = s->a_sgn[RT_J] / QR_FIELD;
+            r.a_sgn[RT_K] = s->a_sgn[RT_K] / QR_FIELD;
+            r.a_sgn[RT_L] = s->a_sgn[RT_L] / QR_FIELD;
+
+            for (int t = 0; t < 4; t++)
+            {
+                r.srf_t[t] = s->srf_t[t];
+            }
+            r.conic     = (int32_t)(rt_cell)s->msc_p[1];
+            r.clip_head = list_head((const rt_ELEM *)s->msc_p[2], LIST_CLIP);
+            r.trnode    = surface((const rt_SIMD_SURFACE *)s->msc_p[3]);
+
+            r.mat[0]    = material((const rt_SIMD_MATERIAL *)s->mat_p[0]);
+            r.props[0]  = (int32_t)(rt_cell)s->mat_p[1];
+            r.mat[1]    = material((const rt_SIMD_MATERIAL *)s->mat_p[2]);
+            r.props[1]  = (int32_t)(rt_cell)s->mat_p[3];
+
+            r.lst_lgt[0] = list_head((const rt_ELEM *)s->lst_p[0], LIST_LIGHT);
+            r.lst_srf[0] = list_head((const rt_ELEM *)s->lst_p[1], LIST_SURF);
+            r.lst_lgt[1] = list_head((const rt_ELEM *)s->lst_p[2], LIST_LIGHT);
+            r.lst_srf[1] = list_head((const rt_ELEM *)s->lst_p[3], LIST_SURF);
+
+            surfs.push_back(r);
+        }
+    }
+
+    /* "next" links once every element has its index */
+    for (size_t i = 0; i < elems.size(); i++)
+    {
+        const rt_ELEM *n = elem_src[i]->next;
+        elems[i].next = n == RT_NULL ? QR_NIL : elem_idx[n];
+    }
+}
+
+static uint32_t align16(uint32_t v)
+{
+    return (v + 15u) & ~15u;
+}
+
+const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
+{
+    const rt_SIMD_CONTEXT *s_ctx = (const rt_SIMD_CONTEXT *)s_inf->ctx;
+    const rt_SIMD_CAMERA  *s_cam = (const rt_SIMD_CAMERA *)s_inf->cam;
+
+    if (s_ctx == RT_NULL || s_cam == RT_NULL || s_inf->tiles == RT_NULL)
+    {
+        throw rt_Exception("null-pointer in qr_Flattener::build");
+    }
+    if (s_inf->pt_on != 0)
+    {
+        throw rt_Exception("path-tracer mode is not supported by B200 backend");
+    }
+
+    elem_idx.clear(); surf_idx.clear(); mat_idx.clear();
+    lgt_idx.clear();  tex_idx.clear();
+    elem_src.clear(); elem_kind.clear(); surf_src.clear();
+    elems.clear(); surfs.clear(); mats.clear(); lgts.clear();
+    texels.clear(); tiles.clear();
+    surf_done = 0;
+
+    qr_blob_header h;
+    memset(&h, 0, sizeof(h));
+    h.magic   = QR_BLOB_MAGIC;
+    h.version = QR_BLOB_VERSION;
+
+    h.x_res   = (int32_t)s_inf->frm_w;
+    h.y_res   = (int32_t)s_inf->frm_h;
+    h.x_row   = (int32_t)s_inf->frm_row;
+    h.fsaa    = (int32_t)s_inf->fsaa;
+    h.depth   = (int32_t)s_inf->depth;
+    h.tile_w  = (int32_t)s_inf->tile_w;
+    h.tile_h  = (int32_t)s_inf->tile_h;
+    h.tls_row = (int32_t)s_inf->tls_row;
+    h.tls_col = (h.y_res + h.tile_h - 1) / h.tile_h;
+    h.lst_head = QR_NIL; /* inf_LST is only read when RT_FEAT_TILING == 0 */
+
+    h.ctx_flags = (uint32_t)s_ctx->param[1];
+    h.t_min  = s_ctx->t_min[0];
+    h.org[0] = s_ctx->org_x[0];
+    h.org[1] = s_ctx->org_y[0];
+    h.org[2] = s_ctx->org_z[0];
+
+    h.cam_t_max = s_cam->t_max[0];
+    h.dir[0] = s_cam->dir_x[0]; h.dir[1] = s_cam->dir_y[0]; h.dir[2] = s_cam->dir_z[0];
+    h.hor[0] = s_cam->hor_x[0]; h.hor[1] = s_cam->hor_y[0]; h.hor[2] = s_cam->hor_z[0];
+    h.ver[0] = s_cam->ver_x[0]; h.ver[1] = s_cam->ver_y[0]; h.ver[2] = s_cam->ver_z[0];
+    for (int i = 0; i < 4; i++)
+    {
+        h.hor_a[i] = s_cam->hor_a[i];
+        h.ver_a[i] = s_cam->ver_a[i];
+    }
+    h.amb[0] = s_cam->col_r[0];
+    h.amb[1] = s_cam->col_g[0];
+    h.amb[2] = s_cam->col_b[0];
+    h.cam_clamp = s_cam->clamp[0];
+    h.cam_cmask = (uint32_t)s_cam->cmask[0];
+
+    /* the integer pixel indices of lane i (engine.cpp:3465-3550) are
+     * re-derived on the device from fsaa; make sure they are what we expect */
+    {
+        const int lane[3][4] = { {0, 1, 2, 3}, {0, 0, 1, 1}, {0, 0, 0, 0} };
+        if (h.fsaa < 0 || h.fsaa > 2)
+        {
+            throw rt_Exception("unsupported fsaa mode in qr_Flattener::build");
+        }
+        for (int i = 0; i < 4; i++)
+        {
+            if (s_inf->hor_c[i] != (rt_real)lane[h.fsaa][i])
+            {
+                throw rt_Exception("unexpected hor_c in qr_Flattener::build");
+            }
+        }
+    }
+
+    /* tiles */
+    rt_ELEM **tl = (rt_ELEM **)s_inf->tiles;
+    int32_t n_tiles = h.tls_row * h.tls_col;
+    tiles.resize(n_tiles);
+    for (int32_t t = 0; t < n_tiles; t++)
+    {
+        tiles[t] = list_head(tl[t], LIST_SURF);
+    }
+    drain();
+
+    h.n_surf   = (int32_t)surfs.size();
+    h.n_mat    = (int32_t)mats.size();
+    h.n_lgt    = (int32_t)lgts.size();
+    h.n_elem   = (int32_t)elems.size();
+    h.n_tiles  = n_tiles;
+    h.n_texels = (int32_t)texels.size();
+
+    uint32_t off = sizeof(qr_blob_header);
+    h.off_surf   = off; off = align16(off + h.n_surf   * sizeof(qr_surface));
+    h.off_mat    = off; off = align16(off + h.n_mat    * sizeof(qr_material));
+    h.off_lgt    = off; off = align16(off + h.n_lgt    * sizeof(qr_light));
+    h.off_elem   = off; off = align16(off + h.n_elem   * sizeof(qr_elem));
+    h.off_tiles  = off; off = align16(off + h.n_tiles  * sizeof(int32_t));
+    h.off_texels = off; off = align16(off + h.n_texels * sizeof(uint32_t));
+    h.total_bytes = off;
+
+    blob.assign(off, 0);
+    memcpy(&blob[0], &h, sizeof(h));
+    if (h.n_surf)   memcpy(&blob[h.off_surf],   &surfs[0],  h.n_surf   * sizeof(qr_surface));
+    if (h.n_mat)    memcpy(&blob[h.off_mat],    &mats[0],   h.n_mat    * sizeof(qr_material));
+    if (h.n_lgt)    memcpy(&blob[h.off_lgt],    &lgts[0],   h.n_lgt    * sizeof(qr_light));
+    if (h.n_elem)   memcpy(&blob[h.off_elem],   &elems[0],  h.n_elem   * sizeof(qr_elem));
+    if (h.n_tiles)  memcpy(&blob[h.off_tiles],  &tiles[0],  h.n_tiles  * sizeof(int32_t));
+    if (h.n_texels) memcpy(&blob[h.off_texels], &texels[0], h.n_texels * sizeof(uint32_t));
+
+    *bytes = blob.size();
+    return &blob[0];
+}
