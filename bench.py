@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the render0 path.
+
+Workload (BASELINE.json configs[1]): RooT's default demo scene scn_demo03,
+1920x1080, 4x antialiasing + gamma, camera 0, time 0 -- the scene blob of
+tests/golden/demo03_1080p_a4g.npz (flattened from the reference engine by
+tools/make_golden.py; synthetic in the sense that nothing is loaded from a
+dataset: the scene is the reference's statically linked demo data).
+
+A step = one render0 pass over one frame (8 294 400 primary samples).
+
+  value   total rays / s (primary + shadow + reflection + refraction rays of the
+          shade-once algorithm, 36.2 M per frame) with the scene already in
+          HBM; device time from CUDA events on the launching stream
+  e2e     same metric through the C ABI with HOST buffers: qr_scene_upload
+          (pinned staging + H2D) + qr_render (kernel + D2H of the frame)
+  roofline  algorithmic IEEE fp32 operations per frame (counted by the device
+          core compiled for the host, tools/make_golden.py) / kernel time,
+          against the measured non-FMA FP32 rate of this GPU (qr_fp32_peak)
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/qr_ref_harness, AVX-512
+          if the host has it, all host threads) on the same frame, render-only
+
+  --impl reference   times only the reference's CPU implementation.
+
+N > 1 (torchrun, one rank per GPU): tile rows are split into contiguous bands
+(strong scaling of one frame), every rank renders its band, bands are gathered
+on rank 0 over NCCL.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "demo03_1080p_a4g"
+WORKLOAD_DESC = "scn_demo03 (RooT default demo scene) 1920x1080 4xAA + gamma, camera 0, t=0"
+METRIC = "Mrays/s at 1080p 4xAA (frame ms = ms_per_step)"
+UNIT = "Mrays/s"
+REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "qr_ref_harness")
+REF_ARGS = ["-s", "demo03", "-x", "1920", "-y", "1080", "-a", "2", "-g", "-u"]
+
+
+# ---------------------------------------------------------------- helpers ---
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for raw in self.proc.stdout:
+            self.lines.append(raw.decode(errors="replace").strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_workload():
+    import __graft_entry__ as ge
+    blob, ref_frame, meta = ge.load_golden(WORKLOAD)
+    return ge, blob, ref_frame, meta
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(frames, warmup, threads):
+    """The unmodified reference on the host cores; returns dict or None."""
+    if not os.path.exists(REF_HARNESS):
+        return None
+    cmd = [REF_HARNESS] + REF_ARGS + ["-t", str(threads), "-f", str(frames), "-w", str(warmup)]
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, check=True)
+        return json.loads(out.stdout.decode().strip().splitlines()[-1])
+    except Exception as exc:      # binary not runnable on this host
+        sys.stderr.write("reference harness failed: %r\n" % (exc,))
+        return None
+
+
+def run_port(blob, meta, rows):
+    """Fallback CPU baseline: the oracle port, one thread, a band of rows."""
+    import __graft_entry__ as ge
+    t0 = time.perf_counter()
+    _, _, st = ge.oracle_render(blob, packet=32, y0=0, y1=rows)
+    dt = time.perf_counter() - t0
+    frac = rows / float(meta["y_res"])
+    return dt / frac
+
+
+def cpu_baseline(blob, meta, frames, warmup):
+    """cpu_baseline object: the reference timed on this box's host cores."""
+    rays = meta["rays"]["total"]
+    threads = min(host_threads(), 120)
+    ref = run_reference(frames, warmup, threads)
+    if ref is not None:
+        ms = ref["ms_med"]
+        return {"value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "cores": ref["threads"],
+                "kind": "reference", "frame_ms": ms, "frame_ms_min": ref["ms_min"],
+                "simd": ref["simd"],
+                "sample": "%d frames (+%d warm-up) of the same 1080p 4xAA demo03 frame, render-only "
+                          "(lists frozen with RT_OPTS_UPDATE_EXT0), %d pinned threads, target %s"
+                          % (frames, warmup, ref["threads"], ref["simd"])}, ms
+    rows = 64
+    sec = run_port(blob, meta, rows)
+    return {"value": rays / sec / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "frame_ms": sec * 1e3,
+            "sample": "oracle port (32-lane packet emulation), rows 0..%d of the frame, scaled" % rows}, sec * 1e3
+
+
+# -------------------------------------------------------- reference arm ---
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    ge, blob, _, meta = load_workload()
+    rays = meta["rays"]["total"]
+    base, ms = cpu_baseline(blob, meta, max(args.steps, 1), max(args.warmup, 0))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC, "rays_per_frame": rays,
+                   "primary_samples_per_frame": meta["rays"]["primary"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------- our arm ---
+
+def main_gpu(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 backend has no CPU fallback")
+
+    ge, blob, ref_frame, meta = load_workload()
+    pkg = ge.load_package()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    ctx = pkg.Context([local_rank])
+    ctx.upload(blob)
+    ctx.sync()
+    hd = ctx.header
+    h, w, x_row = hd["y_res"], hd["x_res"], max(hd["x_row"], hd["x_res"])
+    y0, y1 = pkg.band_rows(h, hd["tile_h"], rank, world)
+    rows_max = max(pkg.band_rows(h, hd["tile_h"], r, world)[1] - pkg.band_rows(h, hd["tile_h"], r, world)[0]
+                   for r in range(world))
+
+    frame_d = torch.zeros((h, x_row), dtype=torch.int32, device=dev)
+    band_d = torch.zeros((rows_max, x_row), dtype=torch.int32, device=dev)
+    gather_d = [torch.zeros((rows_max, x_row), dtype=torch.int32, device=dev) for _ in range(world)] \
+        if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    host_frame = torch.zeros((h, x_row), dtype=torch.int32).pin_memory()
+    qstream = torch.cuda.ExternalStream(ctx.stream(0), device=dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def gather_bands():
+        """bands -> rank 0's frame over NCCL (the one exchange step per frame)."""
+        band_d[: y1 - y0].copy_(frame_d[y0:y1])
+        dist.gather(band_d, gather_list=gather_d, dst=0)
+        if rank == 0:
+            for r in range(1, world):
+                a, b = pkg.band_rows(h, hd["tile_h"], r, world)
+                frame_d[a:b].copy_(gather_d[r][: b - a])
+
+    def step_device(ev0, ev1):
+        flush.fill_(rank + 1)                       # evict L2 between timed iterations
+        qstream.wait_stream(cur)
+        ev0.record(qstream)
+        ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+        if world > 1:
+            cur.wait_stream(qstream)
+            gather_bands()
+            ev1.record(cur)
+        else:
+            ev1.record(qstream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_device(e0, e1)
+    barrier()
+    ctx.ray_counts()
+    launches0 = ctx.launch_count()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        step_device(e0, e1)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    kern_ms = None
+    launches = ctx.launch_count() - launches0
+    counts = ctx.ray_counts()
+
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    rays_t = torch.tensor([float(sum(counts.values()))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    dev_ms = float(t.item())
+    rays_measured = float(rays_t.item()) / args.steps
+    rays = meta["rays"]["total"]
+
+    # parity of what was just timed (rank 0 holds the gathered frame)
+    parity = None
+    if rank == 0:
+        got = frame_d[:, :w].cpu().numpy().view(np.uint32)
+        parity = {"pixels_differ_vs_reference_cpu_frame": int((got != ref_frame).sum()), "pixels": int(got.size)}
+
+    # ---- kernel-only duration for the roofline (N = 1) ----------------------
+    roofline = None
+    peak = None
+    if world == 1:
+        ks = []
+        for _ in range(min(args.steps, 20)):
+            flush.fill_(1)
+            qstream.wait_stream(cur)
+            ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+            ctx.sync()
+            ks.append(ctx.last_render_ms())
+        kern_ms = statistics.mean(ks)
+        peak = ctx.fp32_peak()
+        ops = meta["ieee_ops"]["total"]
+        traffic = None
+        ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(ncu_json):
+            try:
+                traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        achieved = ops / (kern_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "kernel": "qr_render_kernel", "kernel_ms": kern_ms,
+            "algorithmic_ops_per_launch": ops,
+            "peak_source": "measured on this GPU by qr_fp32_peak (separately rounded FMUL+FADD, no FMA; "
+                           "MEASURED_PEAKS.json has no FP32 figure); nominal 148 SM x 128 lanes x 1.965 GHz = 37.2",
+            "hbm_note": "framebuffer write is %.1f MB per launch = %.1f GB/s, far from the HBM bound"
+                        % (h * x_row * 4 / 1e6, h * x_row * 4 / (kern_ms * 1e-3) / 1e9),
+        }
+
+    # ---- end to end through the C ABI with host buffers ----------------------
+    blob_h = np.ascontiguousarray(blob)
+    hf = host_frame.numpy().view(np.uint32)
+    h2d = int(blob_h.size)
+    d2h = int(h * x_row * 4) if rank == 0 else 0
+
+    def step_e2e():
+        if world == 1:
+            ctx.upload(blob_h)
+            ctx.render(hf, x_row)
+        else:
+            ctx.upload(blob_h)
+            qstream.wait_stream(cur)
+            ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+            cur.wait_stream(qstream)
+            gather_bands()
+            if rank == 0:
+                host_frame.copy_(frame_d, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_parity = int((hf[:, :w] != ref_frame).sum()) if rank == 0 else None
+
+    info = ctx.kernel_info()
+    base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base, _ = cpu_baseline(blob, meta, 100, 3)
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        line = {
+            "metric": METRIC, "value": rays * args.steps / (dev_ms * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC, "x_res": w, "y_res": h, "fsaa": "4x", "gamma": True,
+                       "rays_per_frame": rays, "rays_per_frame_measured": rays_measured,
+                       "primary_samples_per_frame": meta["rays"]["primary"],
+                       "primary_Msamples_per_s": meta["rays"]["primary"] * args.steps / (dev_ms * 1e-3) / 1e6,
+                       "l2": "flushed between timed iterations (256 MB fill)",
+                       "sharding": "contiguous tile-row bands per GPU, gather to rank 0" if world > 1 else "single GPU",
+                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+            "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": UNIT,
+                    "ms_per_step": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "path": "qr_scene_upload(host blob) + qr_render(host frame)" if world == 1 else
+                            "qr_scene_upload + qr_render_device band + NCCL gather + D2H on rank 0",
+                    "pixels_differ_vs_reference_cpu_frame": e2e_parity},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "parity": parity,
+            "kernel": info,
+            "wall_s_timed_region": wall,
+        }
+        if roofline is not None:
+            line["roofline"] = roofline
+        if base is not None:
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        sys.stderr.write("bench.py: --gpus %d without torchrun: running the single-process multi-GPU "
+                         "context is not the benchmark contract; launch with torch.distributed.run\n" % args.gpus)
+
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+    return main_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,146 @@
+/*
+ * quadray_b200.h -- C ABI of libquadray_b200.so, the B200 (sm_100a) backend
+ * for QuadRay's core/tracer render0 path.
+ *
+ * The library is the drop-in boundary: plain C, plain pointers and sizes, no
+ * exceptions, no torch types.  It is what the replacement tracer translation
+ * unit (quadray-engine_b200/host/tracer_b200.cpp) calls from inside
+ *
+ *     rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)   core/engine/engine.h:127
+ *                                                          core/tracer/tracer.cpp:5992-6104
+ *
+ * i.e. it replaces the 21 per-SIMD-width instantiations of render0
+ * (core/tracer/tracer.cpp:1081-5405, tracer_*.cpp) and their run-time
+ * dispatch.  The engine-side structures (rt_SIMD_SURFACE, rt_ELEM lists, ...)
+ * are flattened by the caller into the index-based blob of qr_scene_blob.h.
+ *
+ * Every function returns 0 on success or a negative QR_E_* code;
+ * qr_last_error() gives the text.  Nothing here falls back to the CPU: if no
+ * CUDA device is usable qr_init fails.
+ */
+#ifndef QUADRAY_B200_H
+#define QUADRAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "qr_scene_blob.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QR_OK            0
+#define QR_E_ARG        (-1)    /* bad argument */
+#define QR_E_BLOB       (-2)    /* malformed scene blob */
+#define QR_E_CUDA       (-3)    /* CUDA runtime error */
+#define QR_E_NODEV      (-4)    /* no usable CUDA device */
+#define QR_E_STATE      (-5)    /* call order (e.g. render before upload) */
+
+typedef struct qr_ctx qr_ctx;
+
+/*
+ * Create a context on "ndev" CUDA devices (devices == NULL: device 0..ndev-1;
+ * ndev == 0: one device, the current one).  One stream, one pinned staging
+ * area and one device arena per GPU: the per-GPU streams take the place of the
+ * reference's worker threads (rt_FUNC_INIT, core/engine/engine.h:71;
+ * root/RooT_linux.cpp:632-727).
+ */
+int qr_init(const int *devices, int ndev, qr_ctx **out);
+
+/* rt_FUNC_TERM counterpart (engine.h:72): drains the streams, frees everything. */
+void qr_shutdown(qr_ctx *ctx);
+
+/* Text of the last error of this context (ctx == NULL: of the last failed
+ * qr_init on this thread).  Never NULL. */
+const char *qr_last_error(const qr_ctx *ctx);
+
+/*
+ * Hand over the scene for the next frame(s): the flattened equivalent of the
+ * pointer graph reachable from rt_SIMD_INFOX (core/tracer/tracer.h:150-216,
+ * core/engine/engine.cpp:3600-3627).  The blob is copied during the call
+ * (pinned staging, async H2D to every GPU of the context), so the caller may
+ * release its per-frame pools right after (engine.cpp:3317-3323).
+ */
+int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes);
+
+/*
+ * Render the uploaded scene: what pfm->render0(s_inf) does for ALL thread
+ * indices at once (core/engine/engine.cpp:3284-3298, 3627).  Tile rows are
+ * split into contiguous bands across the GPUs of the context, bands are
+ * gathered into GPU 0's framebuffer over NVLink (peer copies).
+ *   frame  != NULL: host framebuffer of y_res rows, "stride" pixels apart
+ *                   (0x00RRGGBB, rt_Scene::get_frame(), engine.cpp:3774-3777);
+ *                   the call returns when it holds the finished frame.
+ *   frame  == NULL: render only (asynchronous; see qr_sync / qr_frame_device).
+ */
+int qr_render(qr_ctx *ctx, uint32_t *frame, int stride);
+
+/*
+ * Render rows [y0, y1) (y0 a multiple of tile_h) into a caller-owned DEVICE
+ * buffer that lives on GPU 0 of the context, asynchronously on the context's
+ * stream.  Used when the consumer is on the GPU and by one-process-per-GPU
+ * drivers that shard tile rows across ranks themselves.
+ */
+int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y1);
+
+/* Wait for all queued work of the context. */
+int qr_sync(qr_ctx *ctx);
+
+/* GPU 0's framebuffer of the last qr_render (x_row-strided) and its stride. */
+int qr_frame_device(qr_ctx *ctx, const uint32_t **frame_dev, int *stride);
+
+/*
+ * "Dump mode": per primary sample hit distance (ctx_T_BUF at XX_end,
+ * core/tracer/tracer.cpp:5161), y_res * x_res * (1 << fsaa) floats, sample-
+ * major within a pixel; +inf where nothing was hit.  Renders one frame.
+ */
+int qr_dump_hits(qr_ctx *ctx, float *t_out);
+
+/*
+ * Rays cast by the renders since the last call (then reset):
+ * counts[0] primary samples, [1] shadow, [2] reflection, [3] refraction rays,
+ * counted where the reference pushes a context (tracer.cpp:2801-2831,
+ * 3486-3532, 3831-3866), for the surface that ends up visible.
+ */
+int qr_ray_counts(qr_ctx *ctx, uint64_t counts[4]);
+
+/* Device time (ms) of the kernels of the last qr_render / qr_render_device,
+ * from CUDA events on the launching stream; max over the GPUs. */
+int qr_last_render_ms(qr_ctx *ctx, float *ms);
+
+/* cudaStream_t of GPU "index" of the context (for event timing by callers). */
+void *qr_stream(qr_ctx *ctx, int index);
+
+/* Number of kernels this library has launched since qr_init. */
+uint64_t qr_launch_count(const qr_ctx *ctx);
+
+/* Static facts about the kernel build: registers, resident CTAs per SM, ... */
+typedef struct qr_kernel_info
+{
+    int sm_count;
+    int threads_per_cta;
+    int ctas_per_sm;
+    int regs_per_thread;
+    int local_bytes_per_thread;
+    int smem_static_bytes;
+    int smem_dynamic_bytes;   /* for the currently uploaded scene, 0 if none */
+    int scene_in_smem;        /* 1 when surfaces/materials/lights are staged */
+} qr_kernel_info;
+
+int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info);
+
+/*
+ * Measured ceiling of the pipe that bounds render0 on this GPU: separately
+ * rounded FP32 multiplies and adds (no FMA contraction, as bit parity with the
+ * reference demands), in 1e12 operations per second, best of a few launches
+ * of a register-resident FMUL/FADD loop on GPU 0 at the clocks of the moment.
+ * It is the denominator of the roofline fraction bench.py reports.
+ */
+int qr_fp32_peak(qr_ctx *ctx, double *tera_ops);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QUADRAY_B200_H */

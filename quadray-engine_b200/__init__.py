@@ -1,0 +1,217 @@
+"""quadray-engine_b200 -- B200-native backend for QuadRay's core/tracer render0 path.
+
+The product is native: CUDA kernels + C ABI in ``lib/libquadray_b200.so``
+(``include/quadray_b200.h``) behind the replacement tracer translation unit
+``host/tracer_b200.cpp``.  This module is only the thin ctypes binding that the
+tests and ``bench.py`` use to call the very same C ABI from Python; it holds no
+rendering logic and has no CPU path -- loading fails loudly when the library
+has not been built, and ``Context()`` fails when there is no CUDA device.
+
+The directory name contains a dash, so import it with
+``__graft_entry__.load_package()`` (importlib by path).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libquadray_b200.so")
+
+QR_OK, QR_E_ARG, QR_E_BLOB, QR_E_CUDA, QR_E_NODEV, QR_E_STATE = 0, -1, -2, -3, -4, -5
+
+# every entry point include/quadray_b200.h declares
+SYMBOLS = (
+    "qr_init", "qr_shutdown", "qr_last_error", "qr_scene_upload", "qr_render",
+    "qr_render_device", "qr_sync", "qr_frame_device", "qr_dump_hits",
+    "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
+    "qr_kernel_query", "qr_fp32_peak",
+)
+
+
+class QuadRayError(RuntimeError):
+    def __init__(self, code, text):
+        RuntimeError.__init__(self, "quadray_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+class KernelInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "sm_count", "threads_per_cta", "ctas_per_sm", "regs_per_thread",
+        "local_bytes_per_thread", "smem_static_bytes", "smem_dynamic_bytes",
+        "scene_in_smem")]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the C-ABI library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run __graft_entry__.build() "
+                          "(nvcc, sm_100a); there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.qr_init.argtypes = [ctypes.POINTER(ci), ci, ctypes.POINTER(vp)]
+    lib.qr_init.restype = ci
+    lib.qr_shutdown.argtypes = [vp]
+    lib.qr_shutdown.restype = None
+    lib.qr_last_error.argtypes = [vp]
+    lib.qr_last_error.restype = ctypes.c_char_p
+    lib.qr_scene_upload.argtypes = [vp, vp, sz]
+    lib.qr_scene_upload.restype = ci
+    lib.qr_render.argtypes = [vp, vp, ci]
+    lib.qr_render.restype = ci
+    lib.qr_render_device.argtypes = [vp, vp, ci, ci, ci]
+    lib.qr_render_device.restype = ci
+    lib.qr_sync.argtypes = [vp]
+    lib.qr_sync.restype = ci
+    lib.qr_frame_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
+    lib.qr_frame_device.restype = ci
+    lib.qr_dump_hits.argtypes = [vp, vp]
+    lib.qr_dump_hits.restype = ci
+    lib.qr_ray_counts.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+    lib.qr_ray_counts.restype = ci
+    lib.qr_last_render_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    lib.qr_last_render_ms.restype = ci
+    lib.qr_stream.argtypes = [vp, ci]
+    lib.qr_stream.restype = vp
+    lib.qr_launch_count.argtypes = [vp]
+    lib.qr_launch_count.restype = ctypes.c_uint64
+    lib.qr_kernel_query.argtypes = [vp, ctypes.POINTER(KernelInfo)]
+    lib.qr_kernel_query.restype = ci
+    lib.qr_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    lib.qr_fp32_peak.restype = ci
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """void* of a numpy array / bytes-like / int device pointer."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.cast(ctypes.c_char_p(bytes(a)), ctypes.c_void_p)
+
+
+class Context(object):
+    """One qr_ctx: the GPUs that render a frame together."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        if devices is None:
+            rc = self.lib.qr_init(None, 0, ctypes.byref(self.h))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.qr_init(arr, len(devices), ctypes.byref(self.h))
+        if rc != QR_OK:
+            text = self.lib.qr_last_error(None).decode()
+            self.h = ctypes.c_void_p()
+            raise QuadRayError(rc, text)
+        self.header = None
+
+    def _check(self, rc):
+        if rc != QR_OK:
+            raise QuadRayError(rc, self.lib.qr_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.qr_shutdown(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, blob):
+        """blob: bytes or uint8 ndarray (host memory)."""
+        if isinstance(blob, np.ndarray):
+            b = np.ascontiguousarray(blob, dtype=np.uint8)
+            self._check(self.lib.qr_scene_upload(self.h, _ptr(b), b.size))
+            raw = b[:256].tobytes()
+        else:
+            raw = bytes(blob)
+            self._check(self.lib.qr_scene_upload(self.h, raw, len(raw)))
+        hdr = np.frombuffer(raw[:256], dtype=np.int32)
+        self.header = {"x_res": int(hdr[4]), "y_res": int(hdr[5]), "x_row": int(hdr[6]),
+                       "fsaa": int(hdr[7]), "depth": int(hdr[8]), "tile_w": int(hdr[9]),
+                       "tile_h": int(hdr[10]), "tls_row": int(hdr[11]), "tls_col": int(hdr[12])}
+
+    def render(self, frame=None, stride=None):
+        """Render into a host uint32 array (rows "stride" pixels apart) or,
+        with frame=None, asynchronously into GPU 0's framebuffer."""
+        if frame is None:
+            self._check(self.lib.qr_render(self.h, None, 0))
+            return None
+        if stride is None:
+            stride = frame.strides[0] // 4 if frame.ndim == 2 else self.header["x_res"]
+        self._check(self.lib.qr_render(self.h, _ptr(frame), int(stride)))
+        return frame
+
+    def render_frame(self):
+        h = self.header
+        out = np.zeros((h["y_res"], h["x_res"]), dtype=np.uint32)
+        return self.render(out, h["x_res"])
+
+    def render_device(self, dev_ptr, stride, y0, y1):
+        self._check(self.lib.qr_render_device(self.h, ctypes.c_void_p(dev_ptr), int(stride), int(y0), int(y1)))
+
+    def sync(self):
+        self._check(self.lib.qr_sync(self.h))
+
+    def frame_device(self):
+        p, s = ctypes.c_void_p(), ctypes.c_int()
+        self._check(self.lib.qr_frame_device(self.h, ctypes.byref(p), ctypes.byref(s)))
+        return p.value, s.value
+
+    def dump_hits(self):
+        h = self.header
+        out = np.zeros((h["y_res"], h["x_res"], 1 << h["fsaa"]), dtype=np.float32)
+        self._check(self.lib.qr_dump_hits(self.h, _ptr(out)))
+        return out
+
+    def ray_counts(self):
+        c = (ctypes.c_uint64 * 4)()
+        self._check(self.lib.qr_ray_counts(self.h, c))
+        return {"primary": int(c[0]), "shadow": int(c[1]), "reflect": int(c[2]), "refract": int(c[3])}
+
+    def last_render_ms(self):
+        ms = ctypes.c_float()
+        self._check(self.lib.qr_last_render_ms(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def stream(self, index=0):
+        return self.lib.qr_stream(self.h, index)
+
+    def launch_count(self):
+        return int(self.lib.qr_launch_count(self.h))
+
+    def fp32_peak(self):
+        """Measured non-FMA FP32 rate of GPU 0, 1e12 ops/s."""
+        t = ctypes.c_double()
+        self._check(self.lib.qr_fp32_peak(self.h, ctypes.byref(t)))
+        return float(t.value)
+
+    def kernel_info(self):
+        k = KernelInfo()
+        self._check(self.lib.qr_kernel_query(self.h, ctypes.byref(k)))
+        return {n: getattr(k, n) for n, _ in KernelInfo._fields_}
+
+
+def band_rows(y_res, tile_h, rank, world):
+    """Tile-row band [y0, y1) of rank "rank" out of "world" (SURVEY.md 8e):
+    contiguous bands of whole tile rows, the same split qr_render uses across
+    the GPUs of one context."""
+    tls_col = (y_res + tile_h - 1) // tile_h
+    t0 = tls_col * rank // world
+    t1 = tls_col * (rank + 1) // world
+    return t0 * tile_h, min(t1 * tile_h, y_res)

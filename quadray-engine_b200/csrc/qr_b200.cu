@@ -1,0 +1,945 @@
+/*
+ * qr_b200.cu -- sm_100a kernels and the C ABI of libquadray_b200.so.
+ *
+ * Kernel qr_render_kernel: a persistent grid (resident CTAs x SM count) whose
+ * WARPS pull work from a device-side tile queue.  A work item is one row of
+ * one screen tile (tile = tile_w x tile_h pixels, core/engine/engine.h:38-39):
+ * the warp walks the row in packets of 32 samples -- 32 >> fsaa adjacent
+ * pixels times 1 << fsaa samples, the very lane layout of the reference's
+ * widest packets (core/engine/engine.cpp:3465-3550) -- so all 32 rays of a
+ * warp share the tile's surface list.  This replaces the scanline interleave
+ * across worker threads (core/tracer/tracer.cpp:1142-1151, 5383-5394).
+ *
+ * Scene staging: header + surfaces + materials + lights (the blob prefix up to
+ * the list elements) are copied into shared memory once per CTA with one TMA
+ * bulk copy (cp.async.bulk + mbarrier complete_tx); list elements, tile heads
+ * and texels are read through L1/L2.
+ *
+ * Epilogue (XX_end, tracer.cpp:5161-5343): clamp, AA halving + pairwise adds
+ * by warp shuffles, gamma, pack; four packed pixels per 128-bit store.
+ */
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <new>
+
+#include "quadray_b200.h"
+#include "qr_core.cuh"
+
+#define QR_CTA_THREADS 256
+#define QR_WARPS       (QR_CTA_THREADS / 32)
+
+/* ------------------------------------------------------------------ PTX --- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src,
+                                             uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok = 0;
+    while (!ok)
+    {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+
+/* --------------------------------------------------------------- kernel --- */
+
+struct qr_launch
+{
+    const uint8_t      *blob;       /* scene blob in global memory */
+    uint32_t           *frame;      /* framebuffer (this GPU) */
+    int                 stride;     /* pixels per framebuffer row */
+    int                 ty0, ty1;   /* band of tile rows [ty0, ty1) */
+    uint32_t            stage_bytes;/* blob prefix staged in smem, 0 = none */
+    unsigned int       *queue;      /* work-item counter */
+    unsigned long long *rays;       /* [4] ray counters */
+    float              *t_out;      /* dump mode, or NULL */
+};
+
+extern __shared__ __align__(128) uint8_t qr_smem[];
+
+__global__ void __launch_bounds__(QR_CTA_THREADS)
+qr_render_kernel(const qr_launch p)
+{
+    __shared__ __align__(8) uint64_t bar;
+
+    const int lane = threadIdx.x & 31;
+
+    /* ---- stage the scene prefix: one elected thread, TMA bulk copies ---- */
+    qr_view v;
+    if (p.stage_bytes != 0)
+    {
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            mbar_expect_tx(&bar, p.stage_bytes);
+            uint32_t off = 0;
+            while (off < p.stage_bytes)
+            {
+                uint32_t n = p.stage_bytes - off;
+                if (n > 32768u) n = 32768u;
+                tma_bulk_g2s(qr_smem + off, p.blob + off, n, &bar);
+                off += n;
+            }
+        }
+        mbar_wait(&bar, 0);
+
+        const qr_blob_header *h = (const qr_blob_header *)qr_smem;
+        v.h      = h;
+        v.surfs  = (const qr_surface  *)(qr_smem + h->off_surf);
+        v.mats   = (const qr_material *)(qr_smem + h->off_mat);
+        v.lgts   = (const qr_light    *)(qr_smem + h->off_lgt);
+        v.elems  = (const qr_elem     *)(p.blob + h->off_elem);
+        v.tiles  = (const int32_t     *)(p.blob + h->off_tiles);
+        v.texels = (const uint32_t    *)(p.blob + h->off_texels);
+    }
+    else
+    {
+        qr_view_init(v, p.blob);
+    }
+
+    const qr_blob_header &h = *v.h;
+    const int fsaa  = h.fsaa;
+    const int ppk   = 32 >> fsaa;                   /* pixels per packet */
+    const int x_res = h.x_res, y_res = h.y_res;
+    const int tiles_x = h.tls_row;
+    const int tile_w = h.tile_w, tile_h = h.tile_h;
+    const int pk_per_row = (tile_w + ppk - 1) / ppk; /* packets per tile row */
+    const unsigned int n_items =
+        (unsigned int)(p.ty1 - p.ty0) * (unsigned int)tiles_x * (unsigned int)tile_h;
+
+    /* lane -> (pixel within packet, sample, AA pattern slot), engine.cpp:3465-3550 */
+    const int lpx   = lane >> fsaa;
+    const int smp   = lane & ((1 << fsaa) - 1);
+    const int lane4 = fsaa == 0 ? (lane & 3)
+                    : fsaa == 1 ? (((lpx & 1) << 1) | smp)
+                    : smp;
+
+    qr_frame stack[QR_STACK_DEPTH + 1];
+    qr_counters cnt;
+    cnt.shadow = cnt.reflect = cnt.refract = 0;
+    unsigned int n_primary = 0;
+
+    for (;;)
+    {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(p.queue, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+
+        const int row  = (int)(item % (unsigned int)tile_h);
+        const int tile = (int)(item / (unsigned int)tile_h);
+        const int ty   = p.ty0 + tile / tiles_x;
+        const int tx   = tile % tiles_x;
+        const int y    = ty * tile_h + row;
+        if (y >= y_res) continue;
+
+        for (int pk = 0; pk < pk_per_row; pk++)
+        {
+            const int x0 = tx * tile_w + pk * ppk;  /* first pixel of the packet */
+            if (x0 >= x_res) break;
+            const int px = x0 + lpx;
+
+            float col[3] = {0.0f, 0.0f, 0.0f};
+            float t = 0.0f;
+            const bool live = px < x_res;
+            if (live)
+            {
+                qr_trace_sample(v, px, y, lane4, stack, col, &t, &cnt);
+                n_primary++;
+                if (p.t_out != NULL)
+                {
+                    p.t_out[(((size_t)y * x_res + px) << fsaa) + smp] = t;
+                }
+            }
+            __syncwarp();
+
+            /* XX_end: clamp, then AA passes of halve + add adjacent pairs */
+            float r = qr_clamp1(col[0]), g = qr_clamp1(col[1]), b = qr_clamp1(col[2]);
+            for (int pass = 0; pass < fsaa; pass++)
+            {
+                const int d = 1 << pass;
+                r = qr_mul(r, 0.5f); g = qr_mul(g, 0.5f); b = qr_mul(b, 0.5f);
+                const float r2 = __shfl_xor_sync(0xFFFFFFFFu, r, d);
+                const float g2 = __shfl_xor_sync(0xFFFFFFFFu, g, d);
+                const float b2 = __shfl_xor_sync(0xFFFFFFFFu, b, d);
+                /* the lower lane of the pair is the left operand of the add */
+                if ((lane & d) == 0)
+                {
+                    r = qr_add(r, r2); g = qr_add(g, g2); b = qr_add(b, b2);
+                }
+                else
+                {
+                    r = qr_add(r2, r); g = qr_add(g2, g); b = qr_add(b2, b);
+                }
+            }
+            const uint32_t pix = qr_pack(h, r, g, b);
+
+            /* pixel q of the packet sits in lane q << fsaa; lanes 0..ppk/4-1
+             * collect four pixels each and issue one 128-bit store */
+            uint32_t q4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                q4[j] = __shfl_sync(0xFFFFFFFFu, pix, (((lane << 2) + j) << fsaa) & 31);
+            }
+            if (lane < (ppk >> 2))
+            {
+                const int xq = x0 + (lane << 2);
+                uint32_t *dst = p.frame + (size_t)y * p.stride + xq;
+                if (xq + 3 < x_res && ((((size_t)y * p.stride + xq) & 3) == 0))
+                {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+                }
+                else
+                {
+                    for (int j = 0; j < 4; j++)
+                    {
+                        if (xq + j < x_res) dst[j] = q4[j];
+                    }
+                }
+            }
+        }
+    }
+
+    /* ray counters: warp-reduce, one atomic per warp and kind */
+    unsigned int c0 = n_primary, c1 = cnt.shadow, c2 = cnt.reflect, c3 = cnt.refract;
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d);
+        c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
+        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d);
+        c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
+    }
+    if (lane == 0)
+    {
+        atomicAdd(&p.rays[0], (unsigned long long)c0);
+        atomicAdd(&p.rays[1], (unsigned long long)c1);
+        atomicAdd(&p.rays[2], (unsigned long long)c2);
+        atomicAdd(&p.rays[3], (unsigned long long)c3);
+    }
+}
+
+/*
+ * FP32 pipe ceiling probe: 8 independent chains per thread of x = x * a + b
+ * issued as separate FMUL and FADD (never FFMA), all in registers.
+ */
+__global__ void __launch_bounds__(256)
+qr_fp32_peak_kernel(float *out, float a, float b, int iters)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f;
+    float x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++)
+    {
+        x0 = __fadd_rn(__fmul_rn(x0, a), b); x1 = __fadd_rn(__fmul_rn(x1, a), b);
+        x2 = __fadd_rn(__fmul_rn(x2, a), b); x3 = __fadd_rn(__fmul_rn(x3, a), b);
+        x4 = __fadd_rn(__fmul_rn(x4, a), b); x5 = __fadd_rn(__fmul_rn(x5, a), b);
+        x6 = __fadd_rn(__fmul_rn(x6, a), b); x7 = __fadd_rn(__fmul_rn(x7, a), b);
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;       /* keep the chains alive */
+}
+
+/* ------------------------------------------------------------ host side --- */
+
+#define QR_MAX_DEV 16
+
+struct qr_dev
+{
+    int             id;
+    cudaStream_t    stream;
+    cudaEvent_t     ev0, ev1, done;
+    uint8_t        *blob_d;     size_t blob_cap;
+    uint8_t        *blob_h;     size_t blob_hcap;   /* pinned staging (dev 0 only) */
+    uint32_t       *frame_d;    size_t frame_cap;   /* bytes */
+    uint32_t       *frame_h;    size_t frame_hcap;  /* pinned (dev 0 only) */
+    float          *t_d;        size_t t_cap;
+    unsigned int   *queue_d;
+    unsigned long long *rays_d;
+    int             sm_count;
+    int             ctas_per_sm;
+    int             smem_optin;
+    int             ty0, ty1;
+    bool            timed;
+};
+
+struct qr_ctx
+{
+    int             ndev;
+    qr_dev          dev[QR_MAX_DEV];
+    qr_blob_header  hdr;
+    bool            have_scene;
+    uint32_t        stage_bytes;
+    uint64_t        launches;
+    uint64_t        rays[4];
+    cudaFuncAttributes fattr;
+    char            err[512];
+};
+
+static thread_local char g_init_err[512] = "";
+
+static int qr_fail(qr_ctx *ctx, int code, const char *fmt, ...)
+{
+    char *dst = ctx != NULL ? ctx->err : g_init_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define QR_CUDA(ctx, call)                                                   \
+    do                                                                       \
+    {                                                                        \
+        cudaError_t e_ = (call);                                             \
+        if (e_ != cudaSuccess)                                               \
+        {                                                                    \
+            return qr_fail(ctx, QR_E_CUDA, "%s failed: %s (%s:%d)", #call,   \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);      \
+        }                                                                    \
+    }                                                                        \
+    while (0)
+
+extern "C" const char *qr_last_error(const qr_ctx *ctx)
+{
+    return ctx != NULL ? ctx->err : g_init_err;
+}
+
+extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
+{
+    if (out == NULL || ndev < 0 || ndev > QR_MAX_DEV)
+    {
+        return qr_fail(NULL, QR_E_ARG, "qr_init: bad arguments");
+    }
+    *out = NULL;
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+    {
+        return qr_fail(NULL, QR_E_NODEV, "qr_init: no CUDA device (%s); this "
+                       "backend has no CPU fallback", cudaGetErrorString(e));
+    }
+
+    qr_ctx *ctx = new (std::nothrow) qr_ctx();
+    if (ctx == NULL)
+    {
+        return qr_fail(NULL, QR_E_ARG, "qr_init: out of memory");
+    }
+    memset(ctx, 0, sizeof(*ctx));
+
+    int cur = 0;
+    cudaGetDevice(&cur);
+    ctx->ndev = ndev == 0 ? 1 : ndev;
+
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        d.id = devices != NULL ? devices[i] : (ndev == 0 ? cur : i);
+        if (d.id < 0 || d.id >= count)
+        {
+            int rc = qr_fail(NULL, QR_E_NODEV, "qr_init: device %d not present (%d visible)", d.id, count);
+            delete ctx;
+            return rc;
+        }
+    }
+
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(d.id)) != cudaSuccess
+        ||  (e = cudaGetDeviceProperties(&prop, d.id)) != cudaSuccess
+        ||  (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess
+        ||  (e = cudaEventCreate(&d.ev0)) != cudaSuccess
+        ||  (e = cudaEventCreate(&d.ev1)) != cudaSuccess
+        ||  (e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming)) != cudaSuccess
+        ||  (e = cudaMalloc(&d.queue_d, sizeof(unsigned int))) != cudaSuccess
+        ||  (e = cudaMalloc(&d.rays_d, 4 * sizeof(unsigned long long))) != cudaSuccess
+        ||  (e = cudaMemset(d.rays_d, 0, 4 * sizeof(unsigned long long))) != cudaSuccess)
+        {
+            int rc = qr_fail(NULL, QR_E_CUDA, "qr_init: device %d setup failed: %s", d.id, cudaGetErrorString(e));
+            qr_shutdown(ctx);
+            return rc;
+        }
+        if (prop.major < 10)
+        {
+            int rc = qr_fail(NULL, QR_E_NODEV, "qr_init: device %d is sm_%d%d; this library is built for sm_100a only",
+                             d.id, prop.major, prop.minor);
+            qr_shutdown(ctx);
+            return rc;
+        }
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_optin = (int)prop.sharedMemPerBlockOptin;
+        d.ctas_per_sm = 1;
+    }
+
+    /* peer access for the framebuffer gather to GPU 0 */
+    for (int i = 1; i < ctx->ndev; i++)
+    {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->dev[i].id, ctx->dev[0].id);
+        if (can)
+        {
+            cudaSetDevice(ctx->dev[i].id);
+            e = cudaDeviceEnablePeerAccess(ctx->dev[0].id, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            {
+                cudaGetLastError();
+            }
+        }
+    }
+
+    cudaSetDevice(ctx->dev[0].id);
+    e = cudaFuncGetAttributes(&ctx->fattr, qr_render_kernel);
+    if (e != cudaSuccess)
+    {
+        int rc = qr_fail(NULL, QR_E_CUDA, "qr_init: kernel image not loadable on device %d: %s",
+                         ctx->dev[0].id, cudaGetErrorString(e));
+        qr_shutdown(ctx);
+        return rc;
+    }
+
+    *out = ctx;
+    return QR_OK;
+}
+
+extern "C" void qr_shutdown(qr_ctx *ctx)
+{
+    if (ctx == NULL)
+    {
+        return;
+    }
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        cudaSetDevice(d.id);
+        if (d.stream)  { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+        if (d.ev0)     cudaEventDestroy(d.ev0);
+        if (d.ev1)     cudaEventDestroy(d.ev1);
+        if (d.done)    cudaEventDestroy(d.done);
+        if (d.blob_d)  cudaFree(d.blob_d);
+        if (d.blob_h)  cudaFreeHost(d.blob_h);
+        if (d.frame_d) cudaFree(d.frame_d);
+        if (d.frame_h) cudaFreeHost(d.frame_h);
+        if (d.t_d)     cudaFree(d.t_d);
+        if (d.queue_d) cudaFree(d.queue_d);
+        if (d.rays_d)  cudaFree(d.rays_d);
+    }
+    delete ctx;
+}
+
+static int qr_check_blob(qr_ctx *ctx, const void *blob, size_t bytes)
+{
+    const qr_blob_header *h = (const qr_blob_header *)blob;
+    if (blob == NULL || bytes < sizeof(qr_blob_header))
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob too small");
+    }
+    if (h->magic != QR_BLOB_MAGIC || h->version != QR_BLOB_VERSION)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob magic/version mismatch");
+    }
+    if (h->total_bytes > bytes || (h->total_bytes & 15) != 0)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob truncated");
+    }
+    if (h->fsaa < 0 || h->fsaa > 2 || h->x_res <= 0 || h->y_res <= 0
+    ||  h->tile_w <= 0 || h->tile_h <= 0 || h->depth < 0 || h->depth > QR_STACK_DEPTH
+    ||  h->tls_row * h->tile_w < h->x_res || h->tls_col * h->tile_h < h->y_res
+    ||  h->n_tiles != h->tls_row * h->tls_col)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob header out of range");
+    }
+    const uint64_t total = h->total_bytes;
+    if ((uint64_t)h->off_surf   + (uint64_t)h->n_surf   * sizeof(qr_surface)  > total
+    ||  (uint64_t)h->off_mat    + (uint64_t)h->n_mat    * sizeof(qr_material) > total
+    ||  (uint64_t)h->off_lgt    + (uint64_t)h->n_lgt    * sizeof(qr_light)    > total
+    ||  (uint64_t)h->off_elem   + (uint64_t)h->n_elem   * sizeof(qr_elem)     > total
+    ||  (uint64_t)h->off_tiles  + (uint64_t)h->n_tiles  * sizeof(int32_t)     > total
+    ||  (uint64_t)h->off_texels + (uint64_t)h->n_texels * sizeof(uint32_t)    > total
+    ||  h->n_surf < 0 || h->n_mat < 0 || h->n_lgt < 0 || h->n_elem < 0 || h->n_texels < 0)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob section out of bounds");
+    }
+    return QR_OK;
+}
+
+static int qr_grow(qr_ctx *ctx, void **ptr, size_t *cap, size_t need, bool pinned)
+{
+    if (*cap >= need)
+    {
+        return QR_OK;
+    }
+    if (*ptr != NULL)
+    {
+        if (pinned) cudaFreeHost(*ptr); else cudaFree(*ptr);
+        *ptr = NULL;
+        *cap = 0;
+    }
+    size_t n = need + need / 4 + 4096;
+    if (pinned)
+    {
+        QR_CUDA(ctx, cudaMallocHost(ptr, n));
+    }
+    else
+    {
+        QR_CUDA(ctx, cudaMalloc(ptr, n));
+    }
+    *cap = n;
+    return QR_OK;
+}
+
+extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    int rc = qr_check_blob(ctx, blob, bytes);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    const qr_blob_header *h = (const qr_blob_header *)blob;
+    const size_t n = h->total_bytes;
+
+    /* pinned staging: the caller's buffer is free again when we return */
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    /* the previous frame's H2D copies read the staging buffer */
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+    }
+    rc = qr_grow(ctx, (void **)&d0.blob_h, &d0.blob_hcap, n, true);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    memcpy(d0.blob_h, blob, n);
+
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        rc = qr_grow(ctx, (void **)&d.blob_d, &d.blob_cap, n, false);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+        QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d, d0.blob_h, n, cudaMemcpyHostToDevice, d.stream));
+    }
+
+    ctx->hdr = *h;
+    ctx->have_scene = true;
+
+    /* shared-memory staging of header + surfaces + materials + lights */
+    uint32_t prefix = h->off_elem;
+    const bool contiguous = h->off_surf == sizeof(qr_blob_header)
+                         && h->off_mat >= h->off_surf && h->off_lgt >= h->off_mat
+                         && h->off_elem >= h->off_lgt;
+    const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024;
+    if (contiguous && (prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
+    {
+        ctx->stage_bytes = prefix;
+    }
+    else
+    {
+        ctx->stage_bytes = 0;
+    }
+
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        QR_CUDA(ctx, cudaFuncSetAttribute(qr_render_kernel,
+                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stage_bytes));
+        int nb = 0;
+        QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel,
+                     QR_CTA_THREADS, ctx->stage_bytes));
+        if (nb < 1)
+        {
+            return qr_fail(ctx, QR_E_CUDA, "kernel does not fit on device %d", d.id);
+        }
+        d.ctas_per_sm = nb;
+    }
+    return QR_OK;
+}
+
+static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
+                          int ty0, int ty1, float *t_out)
+{
+    qr_dev &d = ctx->dev[i];
+    QR_CUDA(ctx, cudaSetDevice(d.id));
+    d.timed = false;
+    if (ty1 <= ty0)
+    {
+        return QR_OK;
+    }
+
+    qr_launch p;
+    p.blob = d.blob_d;
+    p.frame = frame_dev;
+    p.stride = stride;
+    p.ty0 = ty0;
+    p.ty1 = ty1;
+    p.stage_bytes = ctx->stage_bytes;
+    p.queue = d.queue_d;
+    p.rays = d.rays_d;
+    p.t_out = t_out;
+
+    const unsigned int n_items = (unsigned int)(ty1 - ty0) * ctx->hdr.tls_row * ctx->hdr.tile_h;
+    unsigned int grid = (unsigned int)(d.sm_count * d.ctas_per_sm);
+    const unsigned int need = (n_items + QR_WARPS - 1) / QR_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+
+    QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
+    QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    qr_render_kernel<<<grid, QR_CTA_THREADS, ctx->stage_bytes, d.stream>>>(p);
+    QR_CUDA(ctx, cudaGetLastError());
+    QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    d.timed = true;
+    ctx->launches++;
+    return QR_OK;
+}
+
+static int qr_collect_rays(qr_ctx *ctx)
+{
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        unsigned long long r[4];
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        QR_CUDA(ctx, cudaMemcpyAsync(r, d.rays_d, sizeof(r), cudaMemcpyDeviceToHost, d.stream));
+        QR_CUDA(ctx, cudaMemsetAsync(d.rays_d, 0, sizeof(r), d.stream));
+        QR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        for (int k = 0; k < 4; k++) ctx->rays[k] += r[k];
+    }
+    return QR_OK;
+}
+
+extern "C" int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y1)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_device: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    if (frame_dev == NULL || stride < h.x_res || y0 < 0 || y1 > h.y_res || y0 > y1
+    ||  (y0 % h.tile_h) != 0)
+    {
+        return qr_fail(ctx, QR_E_ARG, "qr_render_device: bad arguments");
+    }
+    const int ty0 = y0 / h.tile_h;
+    const int ty1 = (y1 + h.tile_h - 1) / h.tile_h;
+    for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
+    return qr_launch_band(ctx, 0, frame_dev, stride, ty0, ty1, NULL);
+}
+
+static int qr_render_all(qr_ctx *ctx, float *t_out_dev)
+{
+    const qr_blob_header &h = ctx->hdr;
+    const int stride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+    const size_t fbytes = (size_t)stride * h.y_res * sizeof(uint32_t);
+    const int ndev = t_out_dev != NULL ? 1 : ctx->ndev;
+    int rc;
+
+    /* GPU 0 owns the full framebuffer; peers render their band into a local
+     * buffer of the same geometry and push it over NVLink */
+    for (int i = 0; i < ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        rc = qr_grow(ctx, (void **)&d.frame_d, &d.frame_cap, fbytes, false);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+        d.ty0 = (int)((long long)h.tls_col * i / ndev);
+        d.ty1 = (int)((long long)h.tls_col * (i + 1) / ndev);
+    }
+    for (int i = ndev; i < ctx->ndev; i++) ctx->dev[i].timed = false;
+
+    for (int i = 0; i < ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        rc = qr_launch_band(ctx, i, d.frame_d, stride, d.ty0, d.ty1, t_out_dev);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+    }
+
+    /* gather: band rows of GPU i -> GPU 0's framebuffer */
+    qr_dev &d0 = ctx->dev[0];
+    for (int i = 1; i < ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        if (d.ty1 <= d.ty0)
+        {
+            continue;
+        }
+        int ya = d.ty0 * h.tile_h, yb = d.ty1 * h.tile_h;
+        if (yb > h.y_res) yb = h.y_res;
+        const size_t off = (size_t)ya * stride;
+        const size_t n = (size_t)(yb - ya) * stride * sizeof(uint32_t);
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        QR_CUDA(ctx, cudaMemcpyPeerAsync(d0.frame_d + off, d0.id, d.frame_d + off, d.id, n, d.stream));
+        QR_CUDA(ctx, cudaEventRecord(d.done, d.stream));
+        QR_CUDA(ctx, cudaSetDevice(d0.id));
+        QR_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d.done, 0));
+    }
+    return QR_OK;
+}
+
+extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    if (frame != NULL && (stride < h.x_res && -stride < h.x_res))
+    {
+        return qr_fail(ctx, QR_E_ARG, "qr_render: stride smaller than x_res");
+    }
+    int rc = qr_render_all(ctx, NULL);
+    if (rc != QR_OK || frame == NULL)
+    {
+        return rc;
+    }
+
+    /* D2H of the finished frame: pinned staging, then rows into the caller's
+     * (possibly bottom-up, negative stride) framebuffer */
+    qr_dev &d0 = ctx->dev[0];
+    const int dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+    const size_t fbytes = (size_t)dstride * h.y_res * sizeof(uint32_t);
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    rc = qr_grow(ctx, (void **)&d0.frame_h, &d0.frame_hcap, fbytes, true);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    QR_CUDA(ctx, cudaMemcpyAsync(d0.frame_h, d0.frame_d, fbytes, cudaMemcpyDeviceToHost, d0.stream));
+    QR_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+    if (stride == dstride)
+    {
+        memcpy(frame, d0.frame_h, fbytes);
+    }
+    else
+    {
+        for (int y = 0; y < h.y_res; y++)
+        {
+            memcpy(frame + (ptrdiff_t)y * stride, d0.frame_h + (size_t)y * dstride,
+                   (size_t)h.x_res * sizeof(uint32_t));
+        }
+    }
+    return QR_OK;
+}
+
+extern "C" int qr_sync(qr_ctx *ctx)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    for (int i = ctx->ndev - 1; i >= 0; i--)
+    {
+        QR_CUDA(ctx, cudaSetDevice(ctx->dev[i].id));
+        QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+    }
+    return QR_OK;
+}
+
+extern "C" int qr_frame_device(qr_ctx *ctx, const uint32_t **frame_dev, int *stride)
+{
+    if (ctx == NULL || frame_dev == NULL || stride == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene || ctx->dev[0].frame_d == NULL)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_frame_device: nothing rendered yet");
+    }
+    *frame_dev = ctx->dev[0].frame_d;
+    *stride = ctx->hdr.x_row >= ctx->hdr.x_res ? ctx->hdr.x_row : ctx->hdr.x_res;
+    return QR_OK;
+}
+
+extern "C" int qr_dump_hits(qr_ctx *ctx, float *t_out)
+{
+    if (ctx == NULL || t_out == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_dump_hits: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    const size_t n = ((size_t)h.x_res * h.y_res) << h.fsaa;
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    int rc = qr_grow(ctx, (void **)&d0.t_d, &d0.t_cap, n * sizeof(float), false);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    rc = qr_render_all(ctx, d0.t_d);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    QR_CUDA(ctx, cudaMemcpyAsync(t_out, d0.t_d, n * sizeof(float), cudaMemcpyDeviceToHost, d0.stream));
+    QR_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+    return QR_OK;
+}
+
+extern "C" int qr_ray_counts(qr_ctx *ctx, uint64_t counts[4])
+{
+    if (ctx == NULL || counts == NULL)
+    {
+        return QR_E_ARG;
+    }
+    int rc = qr_collect_rays(ctx);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    for (int k = 0; k < 4; k++)
+    {
+        counts[k] = ctx->rays[k];
+        ctx->rays[k] = 0;
+    }
+    return QR_OK;
+}
+
+extern "C" int qr_last_render_ms(qr_ctx *ctx, float *ms)
+{
+    if (ctx == NULL || ms == NULL)
+    {
+        return QR_E_ARG;
+    }
+    float best = 0.0f;
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        if (!d.timed)
+        {
+            continue;
+        }
+        float t = 0.0f;
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        QR_CUDA(ctx, cudaEventSynchronize(d.ev1));
+        QR_CUDA(ctx, cudaEventElapsedTime(&t, d.ev0, d.ev1));
+        if (t > best) best = t;
+    }
+    *ms = best;
+    return QR_OK;
+}
+
+extern "C" void *qr_stream(qr_ctx *ctx, int index)
+{
+    if (ctx == NULL || index < 0 || index >= ctx->ndev)
+    {
+        return NULL;
+    }
+    return (void *)ctx->dev[index].stream;
+}
+
+extern "C" uint64_t qr_launch_count(const qr_ctx *ctx)
+{
+    return ctx != NULL ? ctx->launches : 0;
+}
+
+extern "C" int qr_fp32_peak(qr_ctx *ctx, double *tera_ops)
+{
+    if (ctx == NULL || tera_ops == NULL)
+    {
+        return QR_E_ARG;
+    }
+    qr_dev &d = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d.id));
+    const int iters = 8192, grid = d.sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++)
+    {
+        float ms = 0.0f;
+        QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+        qr_fp32_peak_kernel<<<grid, 256, 0, d.stream>>>((float *)d.rays_d, 0.999f, 0.001f, iters);
+        QR_CUDA(ctx, cudaGetLastError());
+        QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+        QR_CUDA(ctx, cudaEventSynchronize(d.ev1));
+        QR_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        ctx->launches++;
+        const double ops = (double)grid * 256.0 * iters * 16.0;
+        const double t = ops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t;
+    }
+    d.timed = false;
+    *tera_ops = best;
+    return QR_OK;
+}
+
+extern "C" int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info)
+{
+    if (ctx == NULL || info == NULL)
+    {
+        return QR_E_ARG;
+    }
+    info->sm_count = ctx->dev[0].sm_count;
+    info->threads_per_cta = QR_CTA_THREADS;
+    info->ctas_per_sm = ctx->dev[0].ctas_per_sm;
+    info->regs_per_thread = ctx->fattr.numRegs;
+    info->local_bytes_per_thread = (int)ctx->fattr.localSizeBytes;
+    info->smem_static_bytes = (int)ctx->fattr.sharedSizeBytes;
+    info->smem_dynamic_bytes = (int)ctx->stage_bytes;
+    info->scene_in_smem = ctx->stage_bytes != 0;
+    return QR_OK;
+}

@@ -70,11 +70,19 @@ QR_HD int32_t qr_cvn(float x)
                                                       : (int32_t)0x80000000u;
 }
 #else
-QR_HD float qr_add(float a, float b) { volatile float r = a + b; return r; }
-QR_HD float qr_sub(float a, float b) { volatile float r = a - b; return r; }
-QR_HD float qr_mul(float a, float b) { volatile float r = a * b; return r; }
-QR_HD float qr_div(float a, float b) { volatile float r = a / b; return r; }
-QR_HD float qr_sqrt(float a)         { return sqrtf(a); }
+/* host build (tests/hostsim): QR_COUNT_OPS tallies the algorithmic IEEE
+ * operations -- the numerator of the FP32 roofline bench.py reports */
+#ifdef QR_COUNT_OPS
+extern unsigned long long qr_ops[4];    /* add/sub, mul, div, sqrt */
+#define QR_OP(i) (qr_ops[i]++)
+#else
+#define QR_OP(i) ((void)0)
+#endif
+QR_HD float qr_add(float a, float b) { QR_OP(0); volatile float r = a + b; return r; }
+QR_HD float qr_sub(float a, float b) { QR_OP(0); volatile float r = a - b; return r; }
+QR_HD float qr_mul(float a, float b) { QR_OP(1); volatile float r = a * b; return r; }
+QR_HD float qr_div(float a, float b) { QR_OP(2); volatile float r = a / b; return r; }
+QR_HD float qr_sqrt(float a)         { QR_OP(3); return sqrtf(a); }
 QR_HD float    qr_u2f(uint32_t u)    { float f; memcpy(&f, &u, 4); return f; }
 QR_HD uint32_t qr_f2u(float f)       { uint32_t u; memcpy(&u, &f, 4); return u; }
 QR_HD int32_t qr_cvm(float x)

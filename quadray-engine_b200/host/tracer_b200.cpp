@@ -1,0 +1,254 @@
+/*
+ * tracer_b200.cpp -- replacement for the reference's core/tracer translation
+ * units (tracer.cpp + the 21 tracer_*.cpp re-includes).
+ *
+ * It defines the three "backend global entry points" that rt_Platform
+ * declares and the reference implements in tracer.cpp (core/engine/engine.h:
+ * 123-127, core/tracer/tracer.h:109-112):
+ *
+ *     rt_si32 rt_Platform::switch0(rt_SIMD_INFOX*, rt_si32 simd)   tracer.cpp:5827-5876
+ *     rt_void rt_Platform::update0(rt_SIMD_SURFACE*)               tracer.cpp:5774-5808
+ *     rt_void rt_Platform::render0(rt_SIMD_INFOX*)                 tracer.cpp:5992-6104
+ *
+ * so the engine (core/engine, core/system), the scene format (format.h) and
+ * the applications (RooT, core_test) link unchanged.  render0 flattens the
+ * engine's per-frame pointer graph into the scene blob (qr_flatten.cpp) and
+ * hands it to libquadray_b200.so through the C ABI of include/quadray_b200.h;
+ * the frame is back in s_inf->frame when it returns, as the callers expect
+ * (engine.cpp:3774-3777, test/core_test.cpp:984, root/RooT.h:597-631).
+ *
+ * There is no CPU path in this file: without a usable B200 render0 throws
+ * rt_Exception.
+ */
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "tracer.h"
+#include "format.h"
+#include "engine.h"
+
+#include "qr_flatten.h"
+#include "quadray_b200.h"
+
+/*
+ * Per-surface solver / normal / clipper dispatch tags and the conic flag,
+ * same rules as tracer.cpp:5774-5808:
+ *   srf_t[0] solver   1 plane, 2 quadric, 3 two-plane (hypercylinder, w == 0)
+ *   srf_t[1] material 1 plane, 2 with linear terms (parabolic family), 3 pure quadratic
+ *   srf_t[2] clipper  same classes as srf_t[1]
+ *   msc_p[1] conic    1 cone / hyperboloid with w == 0, 2 hypercylinder with w == 0
+ */
+rt_void rt_Platform::update0(rt_SIMD_SURFACE *s_srf)
+{
+    rt_ui32 tag = (rt_ui32)(rt_word)s_srf->srf_t[3];
+
+    if (tag >= RT_TAG_SURFACE_MAX)
+    {
+        return;
+    }
+
+    rt_bool quad = tag > RT_TAG_PLANE;
+    rt_bool flat = s_srf->sci_w[0] == 0.0f;
+    rt_bool para = tag == RT_TAG_PARABOLOID || tag == RT_TAG_PARACYLINDER
+                || tag == RT_TAG_HYPERPARABOLOID;
+
+    s_srf->srf_t[0] = !quad ? 1 : (tag == RT_TAG_HYPERCYLINDER && flat) ? 3 : 2;
+    s_srf->srf_t[1] = !quad ? 1 : para ? 2 : 3;
+    s_srf->srf_t[2] = !quad ? 1 : para ? 2 : 3;
+    s_srf->msc_p[1] = (tag == RT_TAG_CONE || (tag == RT_TAG_HYPERBOLOID && flat))
+                    ? (rt_pntr)1
+                    : (tag == RT_TAG_HYPERCYLINDER && flat) ? (rt_pntr)2
+                    : (rt_pntr)0;
+}
+
+/*
+ * The B200 backend has one target: a warp of 32 fp32 lanes.  In the
+ * reference's vocabulary (n_simd x k_size, engine.cpp:628-639) that is the
+ * paired 512-bit target 512x2, width 32 = RT_SIMD_WIDTH of this build, so
+ * get_fsaa_max(), x_row and tile_w rounding (engine.cpp:570, 668-681,
+ * 2833-2839) stay coherent.  A request for any other target is answered with
+ * this one; the applications then report "not supported" themselves
+ * (test/core_test.cpp:907-918).
+ */
+rt_si32 rt_Platform::switch0(rt_SIMD_INFOX *s_inf, rt_si32 simd)
+{
+    s_mask = 0x02000000;
+    s_mode = 0x02000000;
+    return simd_init(4, 2, 2);
+}
+
+/* process-wide GPU context, created by the first render0 */
+static qr_ctx      *g_ctx = RT_NULL;
+static qr_Flattener g_flat;
+static char         g_err[600];
+
+static rt_void qr_throw(rt_pstr what, const qr_ctx *ctx)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, qr_last_error(ctx));
+    throw rt_Exception(g_err);
+}
+
+static rt_void qr_atexit()
+{
+    if (g_ctx != RT_NULL)
+    {
+        qr_shutdown(g_ctx);
+        g_ctx = RT_NULL;
+    }
+}
+
+/*
+ * QR_B200_DEVICES="0,1,2,3" selects the GPUs that share a frame by tile-row
+ * bands (default: the current device only).
+ */
+static rt_void qr_context()
+{
+    if (g_ctx != RT_NULL)
+    {
+        return;
+    }
+
+    int devs[16], ndev = 0;
+    const char *env = getenv("QR_B200_DEVICES");
+    if (env != RT_NULL)
+    {
+        const char *p = env;
+        while (*p != 0 && ndev < 16)
+        {
+            char *end = RT_NULL;
+            long d = strtol(p, &end, 10);
+            if (end == p)
+            {
+                break;
+            }
+            devs[ndev++] = (int)d;
+            p = *end == ',' ? end + 1 : end;
+        }
+    }
+
+    if (qr_init(ndev > 0 ? devs : RT_NULL, ndev, &g_ctx) != QR_OK)
+    {
+        g_ctx = RT_NULL;
+        qr_throw("B200 backend init failed", RT_NULL);
+    }
+    atexit(qr_atexit);
+}
+
+/*
+ * Called once per worker index by render_slice (engine.cpp:3458-3628).  The
+ * whole frame is one GPU submission, so index 0 does the work and the other
+ * indices of the same frame return at once (they would otherwise render the
+ * interleaved rows index, index + thnum, ... tracer.cpp:1142-1151).
+ */
+rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
+{
+    if (s_inf->index != 0)
+    {
+        return;
+    }
+
+    qr_context();
+
+    size_t bytes = 0;
+    const uint8_t *blob = g_flat.build(s_inf, &bytes);
+
+    if (qr_scene_upload(g_ctx, blob, bytes) != QR_OK)
+    {
+        qr_throw("B200 scene upload failed", g_ctx);
+    }
+    if (qr_render(g_ctx, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
+    {
+        qr_throw("B200 render failed", g_ctx);
+    }
+}
+
+/*
+ * engine.cpp:4102-4117, 4162-4308 reference the Fresnel plotters of the
+ * 128v4 target (debug aid behind core_test -z / RooT F-keys, outside the
+ * render0 path).  Scalar statements of the same formulas (the reference's own
+ * RT_PLOT_FUNCS_REF code, tracer.cpp:5413-5434, 5509-5533, 5617-5633,
+ * 5675-5700, shows them in C); they keep plot_funcs() working.
+ */
+namespace simd_128v4
+{
+
+/* unpolarised dielectric reflectance; i_cos is the (negative) ray.normal dot */
+rt_void plot_fresnel(rt_SIMD_INFOP *s_inf)
+{
+    for (int lane = 0; lane < 4; lane++)
+    {
+        const float eta = s_inf->c_rfr[lane];
+        const float ci = -s_inf->i_cos[lane];
+        const float st2 = eta * eta * (1.0f - ci * ci);
+        float refl = 1.0f;                      /* total inner reflection */
+        if (!(st2 > 1.0f))
+        {
+            const float ct = sqrtf(1.0f - st2);
+            const float rs = (eta * ci - ct) / (eta * ci + ct);
+            const float rp = (ci - eta * ct) / (ci + eta * ct);
+            refl = 0.5f * (rs * rs + rp * rp);
+        }
+        s_inf->o_rfl[lane] = refl;
+    }
+}
+
+/* Schlick's polynomial approximation of the same curve */
+rt_void plot_schlick(rt_SIMD_INFOP *s_inf)
+{
+    for (int lane = 0; lane < 4; lane++)
+    {
+        const float eta = s_inf->c_rfr[lane];
+        float cx = -s_inf->i_cos[lane];
+        float base = (eta - 1.0f) / (eta + 1.0f);
+        base = base * base;
+        bool tir = false;
+        if (eta > 1.0f)
+        {
+            const float st2 = eta * eta * (1.0f - cx * cx);
+            tir = st2 > 1.0f;
+            if (!tir) cx = sqrtf(1.0f - st2);
+        }
+        const float w = 1.0f - cx;
+        s_inf->o_rfl[lane] = tir ? 1.0f : base + (1.0f - base) * (w * w) * (w * w) * w;
+    }
+}
+
+/* conductor reflectance, approximate form used by render0 (tracer.cpp:3729-3751) */
+rt_void plot_fresnel_metal_fast(rt_SIMD_INFOP *s_inf)
+{
+    for (int lane = 0; lane < 4; lane++)
+    {
+        const float c  = -s_inf->i_cos[lane];
+        const float n  = s_inf->c_rcp[lane];
+        const float nk = n * n + s_inf->ext_2[lane];
+        const float c2 = c * c;
+        const float tw = 2.0f * n * c;
+        const float rs = (nk - tw + c2) / (nk + tw + c2);
+        const float rp = (nk * c2 - tw + 1.0f) / (nk * c2 + tw + 1.0f);
+        s_inf->o_rfl[lane] = 0.5f * (rs + rp);
+    }
+}
+
+/* conductor reflectance, full form (compiled out of render0: RT_FEAT_FRESNEL_METAL_SLOW is 0) */
+rt_void plot_fresnel_metal_slow(rt_SIMD_INFOP *s_inf)
+{
+    for (int lane = 0; lane < 4; lane++)
+    {
+        const float c   = -s_inf->i_cos[lane];
+        const float n2  = s_inf->c_rcp[lane] * s_inf->c_rcp[lane];
+        const float k2  = s_inf->ext_2[lane];
+        const float c2  = c * c, s2 = 1.0f - c * c;
+        const float u   = n2 - k2 - s2;
+        const float ab  = sqrtf(u * u + 4.0f * n2 * k2);
+        const float a   = sqrtf(0.5f * (ab + u));
+        const float rs  = (ab + c2 - 2.0f * a * c) / (ab + c2 + 2.0f * a * c);
+        const float q   = c2 * ab + s2 * s2, z = 2.0f * a * c * s2;
+        const float rp  = rs * (q - z) / (q + z);
+        s_inf->o_rfl[lane] = 0.5f * (rs + rp);
+    }
+}
+
+}

@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+GOLDEN_ALL = sorted(f[:-4] for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.endswith(".npz"))
+# the 1080p frame is the bench workload; CPU tests use the 800x480 cases
+GOLDEN_SMALL = [g for g in GOLDEN_ALL if "1080p" not in g]
+
+
+@pytest.fixture(scope="session")
+def entry():
+    import __graft_entry__ as ge
+    return ge
+
+
+@pytest.fixture(scope="session")
+def pkg(entry):
+    return entry.load_package()

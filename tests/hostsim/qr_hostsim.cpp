@@ -9,7 +9,15 @@
  */
 #include <stdlib.h>
 #include <stdint.h>
+#define QR_COUNT_OPS
+unsigned long long qr_ops[4] = {0, 0, 0, 0};
 #include "qr_core.cuh"
+
+/* algorithmic IEEE op counts since the last call: add/sub, mul, div, sqrt */
+extern "C" void qr_hostsim_ops(uint64_t out[4])
+{
+    for (int i = 0; i < 4; i++) { out[i] = qr_ops[i]; qr_ops[i] = 0; }
+}
 
 extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame,
                                  int stride, float *t_out, int y0, int y1,

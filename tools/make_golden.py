@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/.
+
+Runs in the build container only (it needs /root/reference through the two
+binaries oracle/Makefile builds):
+
+  oracle/_ref/qr_ref_harness     the UNMODIFIED reference core -> reference frame
+  oracle/_ref/qr_oracle_harness  reference engine + this repo's flattener
+                                 -> scene blob of the very same frame
+
+Each fixture is tests/golden/<name>.npz with
+  blob   uint8   scene blob (include/qr_scene_blob.h)
+  frame  uint32  y_res x x_res reference frame (0x00RRGGBB), rendered by the
+                 reference's auto-selected SIMD target (512x2v2 here)
+  meta   json    harness arguments, reference target, ray counts
+
+The reference ships no golden images, so these are the pins.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "qr_ref_harness")
+ORC = os.path.join(ROOT, "oracle", "_ref", "qr_oracle_harness")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {}
+for i in range(1, 19):
+    CASES["test%02d_full" % i] = "-s test%02d -p full" % i
+CASES.update({
+    "test01_full_a4": "-s test01 -p full -a 2",
+    "test14_full_a4": "-s test14 -p full -a 2",
+    "test15_full_a2": "-s test15 -p full -a 1",
+    "test17_full_a4": "-s test17 -p full -a 2",
+    "test18_full_a4": "-s test18 -p full -a 2",
+    "test14_none":    "-s test14 -p none",
+    "test16_none_a4": "-s test16 -p none -a 2",
+    "test05_odd":     "-s test05 -p full -x 403 -y 250 -a 2",
+    "demo01_a4g":     "-s demo01 -a 2 -g",
+    "demo02_a4g":     "-s demo02 -a 2 -g",
+    "demo03_a4g":     "-s demo03 -a 2 -g -b 1000",
+    "demo03_1080p_a4g": "-s demo03 -x 1920 -y 1080 -a 2 -g",
+})
+
+
+def run(cmd, env=None):
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    out = subprocess.run(cmd, env=e, check=True, stdout=subprocess.PIPE).stdout.decode()
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def deferred_counts(blob, w, h, fsaa):
+    """Rays and IEEE operations of the shade-once algorithm the GPU runs,
+    counted by the device core compiled for the host (tests/hostsim)."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libqr_hostsim.so"))
+    lib.qr_hostsim_render.restype = ctypes.c_int
+    lib.qr_hostsim_render.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    frame = np.zeros((h, w), dtype=np.uint32)
+    rays = (ctypes.c_uint64 * 4)()
+    ops = (ctypes.c_uint64 * 4)()
+    lib.qr_hostsim_ops(ops)
+    rc = lib.qr_hostsim_render(blob.ctypes.data, blob.size, frame.ctypes.data, w, None, 0, h, rays)
+    assert rc == 0
+    lib.qr_hostsim_ops(ops)
+    r = dict(zip(("primary", "shadow", "reflect", "refract"), [int(x) for x in rays]))
+    r["total"] = sum(r.values())
+    o = dict(zip(("addsub", "mul", "div", "sqrt"), [int(x) for x in ops]))
+    o["total"] = sum(o.values())
+    return frame, r, o
+
+
+def main(names):
+    os.makedirs(OUT, exist_ok=True)
+    for name in names:
+        args = CASES[name].split()
+        with tempfile.TemporaryDirectory() as td:
+            rf, of, bf, sf = (os.path.join(td, n) for n in ("r.raw", "o.raw", "s.blob", "st.json"))
+            jr = run([REF] + args + ["-o", rf])
+            jo = run([ORC] + args + ["-o", of],
+                     {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_STATS": sf})
+            w, h = jr["x_res"], jr["y_res"]
+            frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
+            oframe = np.fromfile(of, dtype=np.uint32).reshape(h, w)
+            blob = np.fromfile(bf, dtype=np.uint8)
+            stats = json.load(open(sf))
+        hframe, rays, ops = deferred_counts(blob, w, h, jr["fsaa"])
+        assert np.array_equal(hframe, oframe), name
+        meta = {
+            "name": name, "args": CASES[name], "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
+            "opts": jr["opts"], "ref_simd": jr["simd"],
+            "oracle_packet1_mismatch_vs_ref": int((frame != oframe).sum()),
+            "oracle_immediate_rays": stats,
+            "rays": rays,           # shade-once algorithm (what the GPU casts)
+            "ieee_ops": ops,        # algorithmic IEEE fp32 operations per frame
+        }
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, blob=blob, frame=frame, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print("%-20s %4dx%-4d blob %7d B  npz %7d B  oracle(packet=1) != ref: %d px"
+              % (name, w, h, blob.size, os.path.getsize(path), meta["oracle_packet1_mismatch_vs_ref"]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(CASES))
