@@ -768,7 +768,7 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     }
     QR_CUDA(ctx, cudaMemcpyAsync(d0.frame_h, d0.frame_d, fbytes, cudaMemcpyDeviceToHost, d0.stream));
     QR_CUDA(ctx, cudaStreamSynchronize(d0.stream));
-    if (stride == dstride)
+    if (stride == dstride && dstride == h.x_res)
     {
         memcpy(frame, d0.frame_h, fbytes);
     }
