@@ -30,6 +30,7 @@
 
 #define QR_CTA_THREADS 256
 #define QR_WARPS       (QR_CTA_THREADS / 32)
+#define QR_CTAS_PER_SM 2            /* register budget: 128 per thread */
 
 /* ------------------------------------------------------------------ PTX --- */
 
@@ -87,17 +88,24 @@ struct qr_launch
 
 extern __shared__ __align__(128) uint8_t qr_smem[];
 
-__global__ void __launch_bounds__(QR_CTA_THREADS)
+/*
+ * STAGED = true: the kscene prefix (header, surfaces, shading records,
+ * materials, lights) is copied to shared memory by TMA and every access to it
+ * is derived from the qr_smem symbol, so the compiler emits LDS.128.
+ * STAGED = false (prefix larger than shared memory): everything through L1/L2.
+ */
+template <bool STAGED>
+__global__ void __launch_bounds__(QR_CTA_THREADS, QR_CTAS_PER_SM)
 qr_render_kernel(const qr_launch p)
 {
     __shared__ __align__(8) uint64_t bar;
 
     const int lane = threadIdx.x & 31;
 
-    /* ---- stage the scene prefix: one elected thread, TMA bulk copies ---- */
     qr_view v;
-    if (p.stage_bytes != 0)
+    if (STAGED)
     {
+        /* one elected thread issues the TMA bulk copies, all wait on the mbarrier */
         if (threadIdx.x == 0)
         {
             mbar_init(&bar, 1);
@@ -118,19 +126,11 @@ qr_render_kernel(const qr_launch p)
             }
         }
         mbar_wait(&bar, 0);
-
-        const qr_blob_header *h = (const qr_blob_header *)qr_smem;
-        v.h      = h;
-        v.surfs  = (const qr_surface  *)(qr_smem + h->off_surf);
-        v.mats   = (const qr_material *)(qr_smem + h->off_mat);
-        v.lgts   = (const qr_light    *)(qr_smem + h->off_lgt);
-        v.elems  = (const qr_elem     *)(p.blob + h->off_elem);
-        v.tiles  = (const int32_t     *)(p.blob + h->off_tiles);
-        v.texels = (const uint32_t    *)(p.blob + h->off_texels);
+        qr_view_init(v, qr_smem, p.blob);
     }
     else
     {
-        qr_view_init(v, p.blob);
+        qr_view_init(v, p.blob, p.blob);
     }
 
     const qr_blob_header &h = *v.h;
@@ -180,7 +180,7 @@ qr_render_kernel(const qr_launch p)
             const bool live = px < x_res;
             if (live)
             {
-                qr_trace_sample(v, px, y, lane4, stack, col, &t, &cnt);
+                qr_trace_sample(v, px, y, lane4, stack, col[0], col[1], col[2], t, cnt);
                 n_primary++;
                 if (p.t_out != NULL)
                 {
@@ -427,7 +427,7 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
     }
 
     cudaSetDevice(ctx->dev[0].id);
-    e = cudaFuncGetAttributes(&ctx->fattr, qr_render_kernel);
+    e = cudaFuncGetAttributes(&ctx->fattr, qr_render_kernel<true>);
     if (e != cudaSuccess)
     {
         int rc = qr_fail(NULL, QR_E_CUDA, "qr_init: kernel image not loadable on device %d: %s",
@@ -538,9 +538,11 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         return rc;
     }
     const qr_blob_header *h = (const qr_blob_header *)blob;
-    const size_t n = h->total_bytes;
+    const size_t n = qr_kscene_size(blob);
 
-    /* pinned staging: the caller's buffer is free again when we return */
+    /* pinned staging: the caller's buffer is free again when we return.  The
+     * blob is not copied verbatim: it is compiled into the packed kscene
+     * image (qr_kscene.h) on the way into the staging buffer. */
     qr_dev &d0 = ctx->dev[0];
     QR_CUDA(ctx, cudaSetDevice(d0.id));
     /* the previous frame's H2D copies read the staging buffer */
@@ -553,7 +555,8 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     {
         return rc;
     }
-    memcpy(d0.blob_h, blob, n);
+    qr_kscene_pack(blob, d0.blob_h);
+    const qr_blob_header *kh = (const qr_blob_header *)d0.blob_h;
 
     for (int i = 0; i < ctx->ndev; i++)
     {
@@ -570,13 +573,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     ctx->hdr = *h;
     ctx->have_scene = true;
 
-    /* shared-memory staging of header + surfaces + materials + lights */
-    uint32_t prefix = h->off_elem;
-    const bool contiguous = h->off_surf == sizeof(qr_blob_header)
-                         && h->off_mat >= h->off_surf && h->off_lgt >= h->off_mat
-                         && h->off_elem >= h->off_lgt;
+    /* shared-memory staging of the kscene prefix */
+    const uint32_t prefix = kh->off_elem;
     const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024;
-    if (contiguous && (prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
+    if ((prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
     {
         ctx->stage_bytes = prefix;
     }
@@ -588,12 +588,20 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     for (int i = 0; i < ctx->ndev; i++)
     {
         qr_dev &d = ctx->dev[i];
-        QR_CUDA(ctx, cudaSetDevice(d.id));
-        QR_CUDA(ctx, cudaFuncSetAttribute(qr_render_kernel,
-                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stage_bytes));
         int nb = 0;
-        QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel,
-                     QR_CTA_THREADS, ctx->stage_bytes));
+        QR_CUDA(ctx, cudaSetDevice(d.id));
+        if (ctx->stage_bytes != 0)
+        {
+            QR_CUDA(ctx, cudaFuncSetAttribute(qr_render_kernel<true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stage_bytes));
+            QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel<true>,
+                         QR_CTA_THREADS, ctx->stage_bytes));
+        }
+        else
+        {
+            QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel<false>,
+                         QR_CTA_THREADS, 0));
+        }
         if (nb < 1)
         {
             return qr_fail(ctx, QR_E_CUDA, "kernel does not fit on device %d", d.id);
@@ -633,7 +641,14 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
 
     QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
     QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
-    qr_render_kernel<<<grid, QR_CTA_THREADS, ctx->stage_bytes, d.stream>>>(p);
+    if (ctx->stage_bytes != 0)
+    {
+        qr_render_kernel<true><<<grid, QR_CTA_THREADS, ctx->stage_bytes, d.stream>>>(p);
+    }
+    else
+    {
+        qr_render_kernel<false><<<grid, QR_CTA_THREADS, 0, d.stream>>>(p);
+    }
     QR_CUDA(ctx, cudaGetLastError());
     QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     d.timed = true;

@@ -39,6 +39,7 @@
 
 #include <stdint.h>
 #include "qr_scene_blob.h"
+#include "qr_kscene.h"
 
 #if defined(__CUDACC__)
 #define QR_HD __host__ __device__ __forceinline__
@@ -107,30 +108,35 @@ QR_HD float qr_sgn(float a, int flip) { return flip ? qr_neg(a) : a; }
 QR_HD bool qr_gt(float a, float b) { return !(a <= b); }    /* cgt = NLE */
 QR_HD bool qr_ge(float a, float b) { return !(a <  b); }    /* cge = NLT */
 
-/* ---- scene view ------------------------------------------------------------ */
+/* ---- scene view (packed image, qr_kscene.h) -------------------------------- */
 
 struct qr_view
 {
     const qr_blob_header *h;
-    const qr_surface     *surfs;
-    const qr_material    *mats;
-    const qr_light       *lgts;
+    const qr_f4          *surf;     /* QR_KSURF_QUADS per surface */
+    const qr_f4          *shade;    /* QR_KSHADE_QUADS per surface */
+    const qr_f4          *mat;      /* QR_KMAT_QUADS per material */
+    const qr_f4          *lgt;      /* QR_KLGT_QUADS per light */
     const qr_elem        *elems;
     const int32_t        *tiles;
     const uint32_t       *texels;
 };
 
-QR_HD void qr_view_init(qr_view &v, const void *blob)
+/* "hot" = header + surfaces + shading records + materials + lights (the
+ * kscene prefix, possibly a shared-memory copy), "cold" = the whole image */
+QR_HD void qr_view_init(qr_view &v, const void *hot, const void *cold)
 {
-    const uint8_t *b = (const uint8_t *)blob;
-    const qr_blob_header *h = (const qr_blob_header *)blob;
+    const uint8_t *a = (const uint8_t *)hot;
+    const uint8_t *b = (const uint8_t *)cold;
+    const qr_blob_header *h = (const qr_blob_header *)hot;
     v.h      = h;
-    v.surfs  = (const qr_surface  *)(b + h->off_surf);
-    v.mats   = (const qr_material *)(b + h->off_mat);
-    v.lgts   = (const qr_light    *)(b + h->off_lgt);
-    v.elems  = (const qr_elem     *)(b + h->off_elem);
-    v.tiles  = (const int32_t     *)(b + h->off_tiles);
-    v.texels = (const uint32_t    *)(b + h->off_texels);
+    v.surf   = (const qr_f4 *)(a + h->off_surf);
+    v.shade  = (const qr_f4 *)(a + (uint32_t)h->pad3[0]);
+    v.mat    = (const qr_f4 *)(a + h->off_mat);
+    v.lgt    = (const qr_f4 *)(a + h->off_lgt);
+    v.elems  = (const qr_elem *)(b + h->off_elem);
+    v.tiles  = (const int32_t *)(b + h->off_tiles);
+    v.texels = (const uint32_t *)(b + h->off_texels);
 }
 
 /* ray counters, SURVEY.md 8(d): one ray = one list walk for one sample */
@@ -148,7 +154,7 @@ struct qr_frame
     float   nrm[3];          /* NRM_X/Y/Z */
     float   loc[3];          /* NRM_I/J/K: stored local hit (tracer.cpp:2272-2282) */
     float   c_trn, c_rfl;    /* ctx_C_TRN / ctx_C_RFL */
-    int32_t ei;              /* list element of the surface being shaded */
+    int32_t si;              /* surface being shaded */
     int32_t flg;             /* ctx_LOCAL(FLG): side | props */
     int32_t stage;           /* 0: child is the refraction ray, 1: reflection */
 };
@@ -156,193 +162,175 @@ struct qr_frame
 #define QR_MODE_CLOSEST 0
 #define QR_MODE_SHADOW  1
 
+/* register-resident 3-vectors: component select without local memory */
+QR_HD float qr_pick3(uint32_t i, float a0, float a1, float a2)
+{
+    return i == 0 ? a0 : (i == 1 ? a1 : a2);
+}
+
+QR_HD void qr_put3(uint32_t i, float v, float &a0, float &a1, float &a2)
+{
+    if (i == 0) a0 = v; else if (i == 1) a1 = v; else a2 = v;
+}
+
 /*
  * 3x3 transform, tracer.cpp:1447-1479 / 1512-1548 / 2063-2095: diagonal
  * products first, then the off-diagonal terms of each row in column order;
  * a_map[L] == 1 keeps the diagonal only (scaling fast path).
  */
-QR_HD void qr_xform(const qr_surface &s, float v1, float v2, float v3,
+QR_HD void qr_xform(const qr_f4 *q, uint32_t trm, float v1, float v2, float v3,
                     float &o4, float &o5, float &o6)
 {
-    float x4 = qr_mul(s.tci[0], v1);
-    float x5 = qr_mul(s.tcj[1], v2);
-    float x6 = qr_mul(s.tck[2], v3);
-    if (s.a_map[3] != 1)
+    const qr_f4 q5 = q[5], q6 = q[6];
+    const float tck_z = q[7].x;
+    float x4 = qr_mul(q5.x, v1);
+    float x5 = qr_mul(q6.x, v2);
+    float x6 = qr_mul(tck_z, v3);
+    if (trm != 1)
     {
-        x4 = qr_add(x4, qr_mul(s.tci[1], v2));
-        x4 = qr_add(x4, qr_mul(s.tci[2], v3));
-        x5 = qr_add(x5, qr_mul(s.tcj[0], v1));
-        x5 = qr_add(x5, qr_mul(s.tcj[2], v3));
-        x6 = qr_add(x6, qr_mul(s.tck[0], v1));
-        x6 = qr_add(x6, qr_mul(s.tck[1], v2));
+        x4 = qr_add(x4, qr_mul(q5.y, v2));
+        x4 = qr_add(x4, qr_mul(q5.z, v3));
+        x5 = qr_add(x5, qr_mul(q5.w, v1));
+        x5 = qr_add(x5, qr_mul(q6.y, v3));
+        x6 = qr_add(x6, qr_mul(q6.z, v1));
+        x6 = qr_add(x6, qr_mul(q6.w, v2));
     }
     o4 = x4; o5 = x5; o6 = x6;
-}
-
-/* value of a clipper's implicit function at point p (clipper space),
- * PL_clp 4198-4208, QD_clp 4910-4951, TP_clp 4341-4370 */
-QR_HD bool qr_clip_eval(const qr_surface &cs, int side_data,
-                        const float *px /* NRM_X/Y/Z */, const float *pi /* NRM_I/J/K */,
-                        bool &valid)
-{
-    const float *p = cs.a_sgn[3] ? pi : px;
-    float v;
-    valid = true;
-    if (cs.srf_t[2] == 1)
-    {
-        const int k = cs.a_map[2];
-        v = qr_sgn(k < 3 ? px[k] : pi[k - 3], cs.a_sgn[2]);
-    }
-    else
-    if (cs.srf_t[2] == 2)
-    {
-        float a1 = qr_mul(qr_add(cs.scj[0], cs.scj[0]), p[0]);
-        float a4 = qr_sub(qr_mul(qr_mul(p[0], p[0]), cs.sci[0]), a1);
-        float a2 = qr_mul(qr_add(cs.scj[1], cs.scj[1]), p[1]);
-        float a5 = qr_sub(qr_mul(qr_mul(p[1], p[1]), cs.sci[1]), a2);
-        float a3 = qr_mul(qr_add(cs.scj[2], cs.scj[2]), p[2]);
-        float a6 = qr_sub(qr_mul(qr_mul(p[2], p[2]), cs.sci[2]), a3);
-        a4 = qr_sub(a4, cs.sci[3]);
-        a4 = qr_add(a4, a5);
-        v  = qr_add(a4, a6);
-    }
-    else
-    if (cs.srf_t[2] == 3)
-    {
-        float a4 = qr_mul(qr_mul(p[0], p[0]), cs.sci[0]);
-        float a5 = qr_mul(qr_mul(p[1], p[1]), cs.sci[1]);
-        float a6 = qr_mul(qr_mul(p[2], p[2]), cs.sci[2]);
-        a4 = qr_sub(a4, cs.sci[3]);
-        a4 = qr_add(a4, a5);
-        v  = qr_add(a4, a6);
-    }
-    else
-    {
-        valid = false;
-        return true;
-    }
-    /* APPLY_CLIP 488-496 */
-    return side_data < 0 ? qr_ge(v, 0.0f) : (v <= 0.0f);
 }
 
 /* per-walk transform-caching state (ctx DFF / RAY_IJK / LOCAL(OBJ)) */
 struct qr_walk_state
 {
-    float dff[6];            /* DFF_X/Y/Z, DFF_I/J/K */
-    float rayi[3];           /* RAY_I/J/K */
+    float dx, dy, dz;        /* DFF_X/Y/Z */
+    float di, dj, dk;        /* DFF_I/J/K */
+    float ri, rj, rk;        /* RAY_I/J/K */
     int   l_obj;             /* ctx_LOCAL(OBJ): trnode's last element */
 };
 
 /*
- * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of element "ei".
- * On success "loc" holds the (possibly adjusted) local hit point.
- *   dmask / amask / side: XMISC(PTR) & DMASK lane, AMASK lane, LOCAL(FLG) side
+ * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of a surface whose
+ * quads start at "q" (descriptor "d").  (lrx, ldx) are the ray / diff in the
+ * surface's field set (world or trnode space).  On success lx/ly/lz hold the
+ * (possibly adjusted) local hit point.
  */
-QR_HD bool qr_clip(const qr_view &v, const qr_surface &s, const qr_walk_state &w,
-                   const float *org, const float *ray, float t_min, float t_buf,
-                   float t, bool dmask, uint32_t amask, int side, float *loc)
+QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
+                   float ox, float oy, float oz, float rx, float ry, float rz,
+                   float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
+                   float t_min, float t_buf, float t,
+                   bool dmask, uint32_t amask, int side,
+                   float &lx, float &ly, float &lz)
 {
-    bool m = true;
-    m = m && qr_gt(t_buf, t);
-    m = m && (t_min < t);
+    if (!qr_gt(t_buf, t)) return false;
+    if (!(t_min < t)) return false;
 
-    float hit[3];
-    hit[0] = qr_add(qr_mul(ray[0], t), org[0]);
-    hit[1] = qr_add(qr_mul(ray[1], t), org[1]);
-    hit[2] = qr_add(qr_mul(ray[2], t), org[2]);
+    const float hx = qr_add(qr_mul(rx, t), ox);
+    const float hy = qr_add(qr_mul(ry, t), oy);
+    const float hz = qr_add(qr_mul(rz, t), oz);
 
-    const int shift = s.a_sgn[3];
-    if (s.a_map[3] != 0)
+    if (QR_D_TRM(d) != 0)
     {
-        loc[0] = qr_add(qr_mul(w.rayi[0], t), w.dff[3]);
-        loc[1] = qr_add(qr_mul(w.rayi[1], t), w.dff[4]);
-        loc[2] = qr_add(qr_mul(w.rayi[2], t), w.dff[5]);
+        lx = qr_add(qr_mul(lr0, t), ld0);
+        ly = qr_add(qr_mul(lr1, t), ld1);
+        lz = qr_add(qr_mul(lr2, t), ld2);
     }
     else
     {
-        loc[0] = qr_sub(hit[0], s.pos[0]);
-        loc[1] = qr_sub(hit[1], s.pos[1]);
-        loc[2] = qr_sub(hit[2], s.pos[2]);
+        lx = qr_sub(hx, q0.x);
+        ly = qr_sub(hy, q0.y);
+        lz = qr_sub(hz, q0.z);
     }
 
     /* conic singularity solver 1706-1856 (lane semantics: hmask decides) */
-    if (s.conic != 0 && dmask)
+    const uint32_t conic = QR_D_CONIC(d);
+    if (conic != 0 && dmask)
     {
-        const int iI = s.a_map[0] - shift, iJ = s.a_map[1] - shift, iK = s.a_map[2] - shift;
-        float a0 = qr_mul(loc[iI], loc[iI]);
-        if (s.conic != 2)
+        const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
+        const qr_f4 q1 = q[1];
+        const float t_eps = q[7].z;
+        const float li = qr_pick3(iI, lx, ly, lz), lj = qr_pick3(iJ, lx, ly, lz), lk = qr_pick3(iK, lx, ly, lz);
+        float a0 = qr_mul(li, li);
+        if (conic != 2)
         {
-            a0 = qr_add(a0, qr_mul(loc[iJ], loc[iJ]));
+            a0 = qr_add(a0, qr_mul(lj, lj));
         }
-        a0 = qr_add(a0, qr_mul(loc[iK], loc[iK]));
-        if (a0 < s.t_eps)
+        a0 = qr_add(a0, qr_mul(lk, lk));
+        if (a0 < t_eps)
         {
-            const float *df = w.dff + shift;
-            uint32_t q1 = (qr_f2u(df[iI]) & 0x80000000u) ^ 0x3F800000u;
-            uint32_t q2 = 0;
-            float q3 = s.sci[iI];
+            const float dfi = qr_pick3(iI, ld0, ld1, ld2), dfj = qr_pick3(iJ, ld0, ld1, ld2), dfk = qr_pick3(iK, ld0, ld1, ld2);
+            const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_j = qr_pick3(iJ, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
+            const uint32_t u1 = (qr_f2u(dfi) & 0x80000000u) ^ 0x3F800000u;
+            uint32_t u2 = 0;
+            float q3 = sci_i;
             float q4 = 1.0f;
-            if (s.conic != 2)
+            if (conic != 2)
             {
-                q2 = (qr_f2u(df[iJ]) & 0x80000000u) ^ 0x3F800000u;
-                q3 = qr_add(q3, s.sci[iJ]);
+                u2 = (qr_f2u(dfj) & 0x80000000u) ^ 0x3F800000u;
+                q3 = qr_add(q3, sci_j);
                 q4 = qr_add(q4, 1.0f);
             }
-            q3 = qr_div(q3, s.sci[iK]);
+            q3 = qr_div(q3, sci_k);
             q3 = qr_neg(q3);
             float q6 = q3;
             q3 = qr_sqrt(q3);
             q6 = qr_add(q6, q4);
             q4 = qr_rsq(q6);
-            q4 = qr_mul(q4, s.t_eps);
-            float p1 = qr_mul(qr_u2f(q1), q4);
-            float p2 = qr_mul(qr_u2f(q2), q4);
-            float p3 = qr_mul(q3, q4);
+            q4 = qr_mul(q4, t_eps);
+            const float p1 = qr_mul(qr_u2f(u1), q4);
+            const float p2 = qr_mul(qr_u2f(u2), q4);
+            const float p3 = qr_mul(q3, q4);
             const uint32_t ts = side ? 0x80000000u : 0u;
-            uint32_t u3 = qr_f2u(p3) ^ (qr_f2u(df[iK]) & 0x80000000u);
+            uint32_t u3 = qr_f2u(p3) ^ (qr_f2u(dfk) & 0x80000000u);
             u3 ^= (ts & amask) ^ amask;
             const uint32_t tsn = (ts | amask) ^ amask;
-            loc[iI] = qr_u2f(qr_f2u(p1) ^ tsn);
-            if (s.conic != 2)
+            qr_put3(iI, qr_u2f(qr_f2u(p1) ^ tsn), lx, ly, lz);
+            if (conic != 2)
             {
-                loc[iJ] = qr_u2f(qr_f2u(p2) ^ tsn);
+                qr_put3(iJ, qr_u2f(qr_f2u(p2) ^ tsn), lx, ly, lz);
             }
-            loc[iK] = qr_u2f(u3);
+            qr_put3(iK, qr_u2f(u3), lx, ly, lz);
         }
     }
 
     /* axis min/max 1874-1927 */
-    const int mm = s.minmax_t;
-    if (mm & 1)  m = m && (s.min[0] <= loc[0]);
-    if (mm & 8)  m = m && qr_ge(s.max[0], loc[0]);
-    if (mm & 2)  m = m && (s.min[1] <= loc[1]);
-    if (mm & 16) m = m && qr_ge(s.max[1], loc[1]);
-    if (mm & 4)  m = m && (s.min[2] <= loc[2]);
-    if (mm & 32) m = m && qr_ge(s.max[2], loc[2]);
+    const uint32_t mm = QR_D_MM(d);
+    bool m = true;
+    if (mm != 0)
+    {
+        const qr_f4 q3 = q[3], q4 = q[4];
+        if (mm & 1)  m = m && (q3.x <= lx);
+        if (mm & 8)  m = m && qr_ge(q4.x, lx);
+        if (mm & 2)  m = m && (q3.y <= ly);
+        if (mm & 16) m = m && qr_ge(q4.y, ly);
+        if (mm & 4)  m = m && (q3.z <= lz);
+        if (mm & 32) m = m && qr_ge(q4.z, lz);
+    }
+
+    if (!QR_D_HASCLIP(d))
+    {
+        return m;
+    }
 
     /* custom clippers 1931-2151.  The reference evaluates the whole list for
      * the packet; a lone sample may stop as soon as its mask is clear and no
      * accumulator is open (a cleared mask can only come back through an
      * accum enter/leave pair). */
-    int di = s.clip_head;
-    if (di == QR_NIL)
-    {
-        return m;
-    }
-
-    float nx[3] = {0.0f, 0.0f, 0.0f};           /* NRM_X/Y/Z */
-    float ni[3] = {0.0f, 0.0f, 0.0f};           /* NRM_I/J/K */
-    bool  acc = false, in_acc = false;          /* C_ACC, inside enter..leave */
+    const int s_trnode = (int)qr_f2u(q[4].w);
+    const uint32_t c_def = qr_f2u(q[7].w);
+    float nx = 0.0f, ny = 0.0f, nz = 0.0f;      /* NRM_X/Y/Z */
+    float ni = 0.0f, nj = 0.0f, nk = 0.0f;      /* NRM_I/J/K */
+    bool  acc = false, in_acc = false;
     int   redx = QR_NIL;
-    bool  last = true;                          /* stale Xmm4 stand-in */
+    bool  last = true;
 
-    for (; di != QR_NIL; di = v.elems[di].next)
+    for (int di = (int)qr_f2u(q[3].w); di != QR_NIL; )
     {
         if (!m && !in_acc)
         {
             return false;
         }
         const qr_elem ce = v.elems[di];
+        const int cur = di;
+        di = ce.next;
 
         if (ce.simd == QR_NIL)
         {
@@ -354,58 +342,88 @@ QR_HD bool qr_clip(const qr_view &v, const qr_surface &s, const qr_walk_state &w
             else
             {
                 acc = m;
-                m = s.c_def != 0;
+                m = c_def != 0;
                 in_acc = true;
             }
             continue;
         }
 
-        const qr_surface &cs = v.surfs[ce.simd];
+        const qr_f4 *cq = v.surf + (size_t)ce.simd * QR_KSURF_QUADS;
+        const qr_f4 c0 = cq[0];
+        const uint32_t cd = qr_f2u(c0.w);
         bool have_local = false;
 
-        if (cs.srf_t[3] >= 0)
+        if (!QR_D_ARRAY(cd))
         {
             if (redx != QR_NIL)
             {
-                ni[0] = qr_sub(nx[0], cs.pos[0]);
-                ni[1] = qr_sub(nx[1], cs.pos[1]);
-                ni[2] = qr_sub(nx[2], cs.pos[2]);
-                if (di == redx) redx = QR_NIL;
+                ni = qr_sub(nx, c0.x);
+                nj = qr_sub(ny, c0.y);
+                nk = qr_sub(nz, c0.z);
+                if (cur == redx) redx = QR_NIL;
                 have_local = true;
             }
         }
         else
-        if (ce.simd == s.trnode)
+        if (ce.simd == s_trnode)
         {
-            nx[0] = qr_add(loc[0], s.pos[0]);
-            nx[1] = qr_add(loc[1], s.pos[1]);
-            nx[2] = qr_add(loc[2], s.pos[2]);
+            nx = qr_add(lx, q0.x);
+            ny = qr_add(ly, q0.y);
+            nz = qr_add(lz, q0.z);
             redx = ce.data_p;
             continue;
         }
 
         if (!have_local)
         {
-            nx[0] = qr_sub(hit[0], cs.pos[0]);
-            nx[1] = qr_sub(hit[1], cs.pos[1]);
-            nx[2] = qr_sub(hit[2], cs.pos[2]);
-            if (cs.a_map[3] != 0)
+            nx = qr_sub(hx, c0.x);
+            ny = qr_sub(hy, c0.y);
+            nz = qr_sub(hz, c0.z);
+            if (QR_D_TRM(cd) != 0)
             {
                 float o4, o5, o6;
-                qr_xform(cs, nx[0], nx[1], nx[2], o4, o5, o6);
-                if (cs.srf_t[3] < 0)
+                qr_xform(cq, QR_D_TRM(cd), nx, ny, nz, o4, o5, o6);
+                if (QR_D_ARRAY(cd))
                 {
-                    nx[0] = o4; nx[1] = o5; nx[2] = o6;
+                    nx = o4; ny = o5; nz = o6;
                     redx = ce.data_p;
                     continue;
                 }
-                ni[0] = o4; ni[1] = o5; ni[2] = o6;
+                ni = o4; nj = o5; nk = o6;
             }
         }
 
-        bool valid;
-        bool r = qr_clip_eval(cs, ce.data_i, nx, ni, valid);
-        if (valid) last = r;
+        /* clipper evaluators: PL_clp 4198-4208, QD_clp 4910-4951, TP_clp 4341-4370 */
+        const bool csh = QR_D_SHIFT(cd) != 0;
+        const float p0 = csh ? ni : nx, p1 = csh ? nj : ny, p2 = csh ? nk : nz;
+        const uint32_t ctag = QR_D_CLIP(cd);
+        if (ctag != 0)
+        {
+            float val;
+            if (ctag == 1)
+            {
+                val = qr_sgn(qr_pick3(QR_D_MAP(cd, 2), p0, p1, p2), QR_D_SGN(cd, 2));
+            }
+            else
+            {
+                const qr_f4 c1 = cq[1];
+                float a4 = qr_mul(qr_mul(p0, p0), c1.x);
+                float a5 = qr_mul(qr_mul(p1, p1), c1.y);
+                float a6 = qr_mul(qr_mul(p2, p2), c1.z);
+                if (ctag == 2)
+                {
+                    const qr_f4 c2 = cq[2];
+                    a4 = qr_sub(a4, qr_mul(qr_add(c2.x, c2.x), p0));
+                    a5 = qr_sub(a5, qr_mul(qr_add(c2.y, c2.y), p1));
+                    a6 = qr_sub(a6, qr_mul(qr_add(c2.z, c2.z), p2));
+                }
+                a4 = qr_sub(a4, c1.w);
+                a4 = qr_add(a4, a5);
+                val = qr_add(a4, a6);
+            }
+            /* APPLY_CLIP 488-496 */
+            last = ce.data_i < 0 ? qr_ge(val, 0.0f) : (val <= 0.0f);
+        }
         m = m && last;
     }
     return m;
@@ -415,60 +433,73 @@ QR_HD bool qr_clip(const qr_view &v, const qr_surface &s, const qr_walk_state &w
  * Shadow applicability of a hit, CHECK_SHAD 549-589: light-emitting and
  * fully-transparent non-refractive surfaces do not cast shadows.
  */
-QR_HD bool qr_casts_shadow(int props)
+QR_HD bool qr_casts_shadow(uint32_t props)
 {
     if (props & QR_PROP_LIGHT) return false;
     if ((props & QR_PROP_TRANSP) && !(props & QR_PROP_REFRACT)) return false;
     return true;
 }
 
+QR_HD uint32_t qr_side_props(uint32_t packed, int side)
+{
+    return side ? (packed >> 16) : (packed & 0xFFFFu);
+}
+
 /*
  * One list walk, OO_cyc 1341 .. OO_out 5142, for one sample.
  *   mode CLOSEST: returns true when something was hit; t_buf / best_* updated
  *   mode SHADOW : returns true when the sample is in shadow (first occluder)
- * "ploc" is the stored local hit of the originating level (NRM_I/J/K of the
- * previous context), used when the ray starts on the surface being tested.
+ * (plx, ply, plz) is the stored local hit of the originating level (NRM_I/J/K
+ * of the previous context), used when the ray starts on the surface tested.
  */
 QR_HD bool qr_walk(const qr_view &v, int head, int mode,
-                   const float *org, const float *ray, float t_min, float t_max,
-                   int p_obj, int p_flg, const float *ploc,
-                   float &t_buf, int &best_ei, int &best_side, float *best_loc)
+                   float ox, float oy, float oz, float rx, float ry, float rz,
+                   float t_min, float t_max, int p_obj, int p_flg,
+                   float plx, float ply, float plz,
+                   float &t_buf, int &best_si, int &best_side,
+                   float &blx, float &bly, float &blz)
 {
     qr_walk_state w;
-    w.dff[0] = w.dff[1] = w.dff[2] = w.dff[3] = w.dff[4] = w.dff[5] = 0.0f;
-    w.rayi[0] = w.rayi[1] = w.rayi[2] = 0.0f;
+    w.dx = w.dy = w.dz = w.di = w.dj = w.dk = 0.0f;
+    w.ri = w.rj = w.rk = 0.0f;
     w.l_obj = QR_NIL;
 
     t_buf = t_max;
-    best_ei = QR_NIL;
+    best_si = QR_NIL;
     best_side = 0;
 
-    for (int ei = head; ei != QR_NIL; ei = v.elems[ei].next)
+    int ei = head;
+    while (ei != QR_NIL)
     {
         const qr_elem e = v.elems[ei];
-        const int si = e.simd;
-        const qr_surface &s = v.surfs[si];
-        const bool same = (si == p_obj);
-        const int shift = s.a_sgn[3];
+        const int cur = ei;
+        ei = e.next;
 
-        /* 1352-1373 */
+        const int si = e.simd;
+        const qr_f4 *q = v.surf + (size_t)si * QR_KSURF_QUADS;
+        const qr_f4 q0 = q[0];
+        const uint32_t d = qr_f2u(q0.w);
+        const bool same = (si == p_obj);
+        const bool shift = QR_D_SHIFT(d) != 0;
+        const uint32_t trm = QR_D_TRM(d);
+
+        /* 1352-1373: reuse the stored local hit of the previous context */
         if (same)
         {
-            w.dff[shift + 0] = ploc[0];
-            w.dff[shift + 1] = ploc[1];
-            w.dff[shift + 2] = ploc[2];
+            if (shift) { w.di = plx; w.dj = ply; w.dk = plz; }
+            else       { w.dx = plx; w.dy = ply; w.dz = plz; }
         }
 
-        if (!(s.srf_t[3] < 0) && w.l_obj != QR_NIL)
+        if (!QR_D_ARRAY(d) && w.l_obj != QR_NIL)
         {
             /* 1385-1417: transform caching under a trnode */
             if (!same)
             {
-                w.dff[3] = qr_sub(w.dff[0], s.pos[0]);
-                w.dff[4] = qr_sub(w.dff[1], s.pos[1]);
-                w.dff[5] = qr_sub(w.dff[2], s.pos[2]);
+                w.di = qr_sub(w.dx, q0.x);
+                w.dj = qr_sub(w.dy, q0.y);
+                w.dk = qr_sub(w.dz, q0.z);
             }
-            if (ei == w.l_obj) w.l_obj = QR_NIL;
+            if (cur == w.l_obj) w.l_obj = QR_NIL;
         }
         else
         {
@@ -476,107 +507,113 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
             bool do_ray = same;
             if (!same)
             {
-                w.dff[0] = qr_sub(org[0], s.pos[0]);
-                w.dff[1] = qr_sub(org[1], s.pos[1]);
-                w.dff[2] = qr_sub(org[2], s.pos[2]);
-                if (s.a_map[3] != 0)
+                w.dx = qr_sub(ox, q0.x);
+                w.dy = qr_sub(oy, q0.y);
+                w.dz = qr_sub(oz, q0.z);
+                if (trm != 0)
                 {
                     float o4, o5, o6;
-                    qr_xform(s, w.dff[0], w.dff[1], w.dff[2], o4, o5, o6);
-                    if (s.srf_t[3] < 0)
+                    qr_xform(q, trm, w.dx, w.dy, w.dz, o4, o5, o6);
+                    if (QR_D_ARRAY(d))
                     {
-                        w.dff[0] = o4; w.dff[1] = o5; w.dff[2] = o6;
+                        w.dx = o4; w.dy = o5; w.dz = o6;
                         w.l_obj = e.data_p;
                     }
                     else
                     {
-                        w.dff[3] = o4; w.dff[4] = o5; w.dff[5] = o6;
+                        w.di = o4; w.dj = o5; w.dk = o6;
                     }
                     do_ray = true;
                 }
             }
             if (do_ray)
             {
-                qr_xform(s, ray[0], ray[1], ray[2], w.rayi[0], w.rayi[1], w.rayi[2]);
+                qr_xform(q, trm, rx, ry, rz, w.ri, w.rj, w.rk);
             }
         }
 
-        const float *lray = shift ? w.rayi : ray;       /* RAY at a_sgn[L] */
-        const float *ldff = w.dff + shift;              /* DFF at a_sgn[L] */
+        /* ray / diff in the surface's field set (a_sgn[L] shift) */
+        const float lr0 = shift ? w.ri : rx, lr1 = shift ? w.rj : ry, lr2 = shift ? w.rk : rz;
+        const float ld0 = shift ? w.di : w.dx, ld1 = shift ? w.dj : w.dy, ld2 = shift ? w.dk : w.dz;
 
         /* AR_ptr 3955-4054: bounding volume of an array */
         if (e.data_i == 1)
         {
-            float x1 = lray[0];
-            float x0 = qr_mul(s.sci[0], x1);
-            float x5 = ldff[0];
-            float q7 = qr_mul(s.sci[0], x5);
+            const qr_f4 q1 = q[1];
+            float x1 = lr0;
+            float x0 = qr_mul(q1.x, x1);
+            float x5 = ld0;
+            float q7 = qr_mul(q1.x, x5);
             float x3 = x1;
             x1 = qr_mul(x1, x0); x3 = qr_mul(x3, q7); x5 = qr_mul(x5, q7);
 
-            float x2 = lray[1];
-            x0 = qr_mul(s.sci[1], x2);
-            float x6 = ldff[1];
-            q7 = qr_mul(s.sci[1], x6);
+            float x2 = lr1;
+            x0 = qr_mul(q1.y, x2);
+            float x6 = ld1;
+            q7 = qr_mul(q1.y, x6);
             float x4 = x2;
             x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
             x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
 
-            x2 = lray[2];
-            x0 = qr_mul(s.sci[2], x2);
-            x6 = ldff[2];
-            q7 = qr_mul(s.sci[2], x6);
+            x2 = lr2;
+            x0 = qr_mul(q1.z, x2);
+            x6 = ld2;
+            q7 = qr_mul(q1.z, x6);
             x4 = x2;
             x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
             x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
 
-            x5 = qr_sub(x5, s.sci[3]);
+            x5 = qr_sub(x5, q1.w);
             x5 = qr_mul(x5, x1);
             x3 = qr_mul(x3, x3);
             x3 = qr_sub(x3, x5);
             if (!(0.0f <= x3))
             {
-                ei = e.data_p;                          /* AR_skp */
-                if (ei == w.l_obj) w.l_obj = QR_NIL;
+                /* AR_skp: jump behind the array's last leaf */
+                const int lastleaf = e.data_p;
+                if (lastleaf == w.l_obj) w.l_obj = QR_NIL;
+                ei = v.elems[lastleaf].next;
             }
             continue;
         }
 
-        const int tag = s.srf_t[0];
+        const uint32_t tag = QR_D_TAG(d);
         if (tag == 0) continue;
 
-        float loc[3];
+        float lx, ly, lz;
 
         if (tag == 1)
         {
             /* PL_ptr 4062-4136 */
             if (same) continue;
-            const int k = s.a_map[2];
-            const float dk = qr_neg(qr_sgn(k < 3 ? w.dff[k] : w.dff[k], s.a_sgn[2]));
-            const float rk = qr_sgn(k < 3 ? ray[k] : w.rayi[k - 3], s.a_sgn[2]);
+            const uint32_t k = QR_D_MAP(d, 2), sg = QR_D_SGN(d, 2);
+            const float dk = qr_neg(qr_sgn(qr_pick3(k, ld0, ld1, ld2), sg));
+            const float rk = qr_sgn(qr_pick3(k, lr0, lr1, lr2), sg);
             if (!(0.0f != rk)) continue;
             const float t = qr_div(dk, rk);
-            if (!qr_clip(v, s, w, org, ray, t_min, t_buf, t, false, 0u, 0, loc)) continue;
+            if (!qr_clip(v, q, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
+                         t_min, t_buf, t, false, 0u, 0, lx, ly, lz)) continue;
             const int side = (rk < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
             if (mode == QR_MODE_SHADOW)
             {
-                if (qr_casts_shadow(s.props[side])) return true;
+                if (qr_casts_shadow(qr_side_props(qr_f2u(q[2].w), side))) return true;
                 continue;
             }
-            t_buf = t; best_ei = ei; best_side = side;
-            best_loc[0] = loc[0]; best_loc[1] = loc[1]; best_loc[2] = loc[2];
+            t_buf = t; best_si = si; best_side = side;
+            blx = lx; bly = ly; blz = lz;
             continue;
         }
 
         float a_val, b_val, c_val, d_val;
+        const qr_f4 q1 = q[1];
 
         if (tag == 3)
         {
             /* TP_ptr 4216-4277 */
-            const int iI = s.a_map[0], iK = s.a_map[2];
-            const float sci_i = s.sci[iI - shift], sci_k = s.sci[iK - shift];
-            const float ri = iI < 3 ? ray[iI] : w.rayi[iI - 3], di = w.dff[iI];
-            const float rk = iK < 3 ? ray[iK] : w.rayi[iK - 3], dk = w.dff[iK];
+            const uint32_t iI = QR_D_MAP(d, 0), iK = QR_D_MAP(d, 2);
+            const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
+            const float ri = qr_pick3(iI, lr0, lr1, lr2), di = qr_pick3(iI, ld0, ld1, ld2);
+            const float rk = qr_pick3(iK, lr0, lr1, lr2), dk = qr_pick3(iK, ld0, ld1, ld2);
             float a5 = qr_sub(qr_mul(di, rk), qr_mul(dk, ri));
             a5 = qr_mul(a5, a5);
             a5 = qr_mul(a5, sci_i);
@@ -589,38 +626,30 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
         else
         {
             /* QD_ptr 4378-4447 */
-            float a1 = lray[0];
-            float a0 = qr_mul(s.sci[0], a1);
-            float a5 = ldff[0];
-            float a7 = qr_sub(qr_mul(s.sci[0], a5), s.scj[0]);
-            float a3 = qr_mul(a1, a7);
-            a1 = qr_mul(a1, a0);
-            a7 = qr_sub(a7, s.scj[0]);
-            a5 = qr_mul(a5, a7);
+            const qr_f4 q2 = q[2];
+            float a7 = qr_sub(qr_mul(q1.x, ld0), q2.x);
+            float a3 = qr_mul(lr0, a7);
+            float a1 = qr_mul(lr0, qr_mul(q1.x, lr0));
+            a7 = qr_sub(a7, q2.x);
+            float a5 = qr_mul(ld0, a7);
 
-            float a2 = lray[1];
-            a0 = qr_mul(s.sci[1], a2);
-            float a6 = ldff[1];
-            a7 = qr_sub(qr_mul(s.sci[1], a6), s.scj[1]);
-            float a4 = qr_mul(a2, a7);
-            a2 = qr_mul(a2, a0);
-            a7 = qr_sub(a7, s.scj[1]);
-            a6 = qr_mul(a6, a7);
+            a7 = qr_sub(qr_mul(q1.y, ld1), q2.y);
+            float a4 = qr_mul(lr1, a7);
+            float a2 = qr_mul(lr1, qr_mul(q1.y, lr1));
+            a7 = qr_sub(a7, q2.y);
+            float a6 = qr_mul(ld1, a7);
 
             a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
 
-            a2 = lray[2];
-            a0 = qr_mul(s.sci[2], a2);
-            a6 = ldff[2];
-            a7 = qr_sub(qr_mul(s.sci[2], a6), s.scj[2]);
-            a4 = qr_mul(a2, a7);
-            a2 = qr_mul(a2, a0);
-            a7 = qr_sub(a7, s.scj[2]);
-            a6 = qr_mul(a6, a7);
+            a7 = qr_sub(qr_mul(q1.z, ld2), q2.z);
+            a4 = qr_mul(lr2, a7);
+            a2 = qr_mul(lr2, qr_mul(q1.z, lr2));
+            a7 = qr_sub(a7, q2.z);
+            a6 = qr_mul(ld2, a7);
 
             a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
 
-            a5 = qr_sub(a5, s.sci[3]);
+            a5 = qr_sub(a5, q1.w);
             a_val = a1;
             b_val = a3;
             c_val = a5;
@@ -630,7 +659,7 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
         /* QD_rts 4449-4547 */
         if (!(0.0f <= d_val)) continue;
         const float b = qr_neg(b_val);
-        const bool dmask = d_val < s.d_eps;
+        const bool dmask = d_val < q[7].y;
         const float sd = qr_u2f(qr_f2u(qr_sqrt(d_val)) ^ (qr_f2u(b) & 0x80000000u));
         const float bd = qr_add(b, sd);
         const bool m_pos = 0.0f <= sd;
@@ -654,7 +683,7 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
             float a2 = qr_u2f(qr_f2u(qr_sub(t1, t2)) ^ amask);
             const bool fm = 0.0f <= a2;
             a2 = fm ? a2 : 0.0f;
-            float a5 = qr_abs(qr_mul(fm ? s.t_eps : 0.0f, t1));
+            const float a5 = qr_abs(qr_mul(fm ? q[7].z : 0.0f, t1));
             a2 = qr_sub(qr_mul(a2, -0.5f), a5);
             uint32_t u2 = qr_f2u(a2) ^ amask;
             if (!(k1 && k2)) u2 = 0;
@@ -666,43 +695,47 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
          * "a"; a hit on the first side ends the surface (overdraw check) */
         const int first = qr_gt(0.0f, a_val) ? QR_FLAG_SIDE_INNER : QR_FLAG_SIDE_OUTER;
         const int pf = p_flg & (QR_FLAG_SIDE | QR_FLAG_PASS);
+#pragma unroll 1
         for (int pass = 0; pass < 2; pass++)
         {
             const int side = pass == 0 ? first : (first ^ 1);
             /* CHECK_SIDE 531-540 */
             if (same && (pf == 1 - side || pf == 2 + side)) continue;
             float t; bool k;
-            if (side == QR_FLAG_SIDE_OUTER)
+            if (dmask)
             {
-                if (dmask) { t = t1; k = k1; }
-                else { t = qr_div(t1n, t1d); k = t1d != 0.0f; }
+                t = side == QR_FLAG_SIDE_OUTER ? t1 : t2;
+                k = side == QR_FLAG_SIDE_OUTER ? k1 : k2;
             }
             else
             {
-                if (dmask) { t = t2; k = k2; }
-                else { t = qr_div(t2n, t2d); k = t2d != 0.0f; }
+                const float nn = side == QR_FLAG_SIDE_OUTER ? t1n : t2n;
+                const float dd = side == QR_FLAG_SIDE_OUTER ? t1d : t2d;
+                t = qr_div(nn, dd);
+                k = dd != 0.0f;
             }
             if (!k) continue;
-            if (!qr_clip(v, s, w, org, ray, t_min, t_buf, t, dmask, amask, side, loc)) continue;
+            if (!qr_clip(v, q, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
+                         t_min, t_buf, t, dmask, amask, side, lx, ly, lz)) continue;
             if (mode == QR_MODE_SHADOW)
             {
-                if (qr_casts_shadow(s.props[side])) return true;
+                if (qr_casts_shadow(qr_side_props(qr_f2u(q[2].w), side))) return true;
                 break;
             }
-            t_buf = t; best_ei = ei; best_side = side;
-            best_loc[0] = loc[0]; best_loc[1] = loc[1]; best_loc[2] = loc[2];
+            t_buf = t; best_si = si; best_side = side;
+            blx = lx; bly = ly; blz = lz;
             break;
         }
     }
 
-    return mode == QR_MODE_SHADOW ? false : best_ei != QR_NIL;
+    return mode == QR_MODE_SHADOW ? false : best_si != QR_NIL;
 }
 
 /* texel -> linear colour, PAINT_COLX 664-673 */
-QR_HD float qr_unpack(uint32_t texel, int sh, const qr_material &m, int props)
+QR_HD float qr_unpack(uint32_t texel, int sh, uint32_t cmask, float clamp, uint32_t props)
 {
-    float c = (float)(int32_t)((texel >> sh) & m.cmask);
-    c = qr_div(c, m.clamp);
+    float c = (float)(int32_t)((texel >> sh) & cmask);
+    c = qr_div(c, clamp);
     if (props & QR_PROP_GAMMA) c = qr_mul(c, c);
     return c;
 }
@@ -742,18 +775,19 @@ QR_HD float qr_pow_28_4(float x, uint32_t l_pow)
 }
 
 /* normalise + dot with the normal, tracer.cpp:3216-3246 / 3620-3653 */
-QR_HD float qr_norm_dot(const float *ray, const float *nrm, float *a)
+QR_HD float qr_norm_dot(float rx, float ry, float rz, float nx, float ny, float nz,
+                        float &ax, float &ay, float &az)
 {
-    float s0 = qr_mul(ray[0], ray[0]);
-    s0 = qr_add(s0, qr_mul(ray[1], ray[1]));
-    s0 = qr_add(s0, qr_mul(ray[2], ray[2]));
+    float s0 = qr_mul(rx, rx);
+    s0 = qr_add(s0, qr_mul(ry, ry));
+    s0 = qr_add(s0, qr_mul(rz, rz));
     const float inv = qr_rsq(s0);
-    a[0] = qr_mul(ray[0], inv);
-    a[1] = qr_mul(ray[1], inv);
-    a[2] = qr_mul(ray[2], inv);
-    float d = qr_mul(a[0], nrm[0]);
-    d = qr_add(d, qr_mul(a[1], nrm[1]));
-    d = qr_add(d, qr_mul(a[2], nrm[2]));
+    ax = qr_mul(rx, inv);
+    ay = qr_mul(ry, inv);
+    az = qr_mul(rz, inv);
+    float d = qr_mul(ax, nx);
+    d = qr_add(d, qr_mul(ay, ny));
+    d = qr_add(d, qr_mul(az, nz));
     return d;
 }
 
@@ -761,7 +795,7 @@ QR_HD float qr_norm_dot(const float *ray, const float *nrm, float *a)
 QR_HD float qr_fresnel(float c, float rfr, float x0, float x7)
 {
     float a1 = c;
-    float a2 = qr_sub(qr_mul(a1, rfr), x7);
+    const float a2 = qr_sub(qr_mul(a1, rfr), x7);
     const float a7 = qr_mul(x7, rfr);
     const float a3 = qr_sub(a1, a7);
     a1 = qr_add(a1, a7);
@@ -779,27 +813,27 @@ QR_HD float qr_fresnel(float c, float rfr, float x0, float x7)
  * Returns the sample colour (before clamp / AA / gamma) and the primary T_BUF.
  */
 QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
-                           qr_frame *stack, float *out_col, float *out_t,
-                           qr_counters *cnt)
+                           qr_frame *stack, float &out_r, float &out_g, float &out_b,
+                           float &out_t, qr_counters &cnt)
 {
     const qr_blob_header &h = *v.h;
 
     /* current ray */
-    float org[3], ray[3];
+    float ox, oy, oz, rx, ry, rz;
     float t_min, t_max;
     int   head, mode, p_obj, p_flg;
     int   lvl = 0;
 
     /* shading state of the current level */
-    float lray[3] = {0, 0, 0};      /* RAY of the level (ray[] may hold a shadow ray) */
-    float hit[3] = {0, 0, 0}, nrm[3] = {0, 0, 0}, loc[3] = {0, 0, 0};
-    float tex[3] = {0, 0, 0}, col[3] = {0, 0, 0};
+    float lrx = 0, lry = 0, lrz = 0;    /* RAY of the level (rx.. may hold a shadow ray) */
+    float hx = 0, hy = 0, hz = 0, nx = 0, ny = 0, nz = 0, lcx = 0, lcy = 0, lcz = 0;
+    float tr = 0, tg = 0, tb = 0, cr = 0, cg = 0, cb = 0;
     float dot = 0.0f, c_trn = 0.0f, c_rfl = 0.0f;
-    float xr[3] = {0, 0, 0};
-    int   cur_ei = QR_NIL, l_flg = 0, li = QR_NIL;
+    float xr = 0, xg = 0, xb = 0;
+    int   cur_si = QR_NIL, l_flg = 0, li = QR_NIL;
 
     /* walk results */
-    float t_buf; int best_ei, best_side; float best_loc[3] = {0, 0, 0};
+    float t_buf; int best_si, best_side; float blx = 0, bly = 0, blz = 0;
 
     /* 1287-1322: primary ray; hor_i / ver_i are exact integers */
     {
@@ -807,14 +841,10 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
         float vs = qr_add((float)py, h.ver_a[lane4]);
         hs = qr_add(hs, 0.0f);
         vs = qr_add(vs, 0.0f);
-        for (int k = 0; k < 3; k++)
-        {
-            float a = qr_mul(h.hor[k], hs);
-            float b = qr_mul(h.ver[k], vs);
-            a = qr_add(a, b);
-            ray[k] = qr_add(a, h.dir[k]);
-            org[k] = h.org[k];
-        }
+        rx = qr_add(qr_add(qr_mul(h.hor[0], hs), qr_mul(h.ver[0], vs)), h.dir[0]);
+        ry = qr_add(qr_add(qr_mul(h.hor[1], hs), qr_mul(h.ver[1], vs)), h.dir[1]);
+        rz = qr_add(qr_add(qr_mul(h.hor[2], hs), qr_mul(h.ver[2], vs)), h.dir[2]);
+        ox = h.org[0]; oy = h.org[1]; oz = h.org[2];
         t_min = h.t_min;
         t_max = h.cam_t_max;
         int tx = px / h.tile_w;
@@ -826,16 +856,19 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
     }
 
     float primary_t = t_max;
-    int resume;                     /* 0 none, 1 after refraction, 2 after reflection */
+    int resume;                     /* 0 none, 1 after refraction, 2 after reflection, -1 return */
 
     for (;;)
     {
         /* ---------------- WALK ---------------- */
-        const float *ploc = mode == QR_MODE_SHADOW ? loc
-                          : (lvl > 0 ? stack[lvl - 1].loc : loc);
-        const bool res = qr_walk(v, head, mode, org, ray, t_min, t_max,
-                                 p_obj, p_flg, ploc,
-                                 t_buf, best_ei, best_side, best_loc);
+        float plx = lcx, ply = lcy, plz = lcz;
+        if (mode != QR_MODE_SHADOW && lvl > 0)
+        {
+            plx = stack[lvl - 1].loc[0]; ply = stack[lvl - 1].loc[1]; plz = stack[lvl - 1].loc[2];
+        }
+        const bool res = qr_walk(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
+                                 p_obj, p_flg, plx, ply, plz,
+                                 t_buf, best_si, best_side, blx, bly, blz);
         bool lights_phase = false;
         resume = 0;
 
@@ -845,53 +878,55 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
             const qr_elem le = v.elems[li];
             if (!res)
             {
-                const qr_light &lg = v.lgts[le.simd];
-                const qr_surface &s = v.surfs[v.elems[cur_ei].simd];
-                const qr_material &m = v.mats[s.mat[l_flg & 1]];
-                const int props = l_flg;
+                const qr_f4 *lq = v.lgt + (size_t)le.simd * QR_KLGT_QUADS;
+                const qr_f4 l1 = lq[1], l2 = lq[2];
+                const qr_f4 sh0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
+                const int mi = (int)qr_f2u((l_flg & 1) ? sh0.y : sh0.x);
+                const qr_f4 m2 = v.mat[(size_t)mi * QR_KMAT_QUADS + 2];
+                const uint32_t props = (uint32_t)l_flg;
 
-                /* ray[] holds NEW_X/Y/Z = light vector */
-                float x4 = qr_mul(ray[0], ray[0]);
-                x4 = qr_add(x4, qr_mul(ray[1], ray[1]));
-                x4 = qr_add(x4, qr_mul(ray[2], ray[2]));
+                /* (rx, ry, rz) holds NEW_X/Y/Z = light vector */
+                float x4 = qr_mul(rx, rx);
+                x4 = qr_add(x4, qr_mul(ry, ry));
+                x4 = qr_add(x4, qr_mul(rz, rz));
                 const float r2 = x4;
-                float d, x6;
+                float dd, x6;
                 if (props & QR_PROP_DIFFUSE)
                 {
-                    d = dot;
+                    dd = dot;
                     x6 = x4;
                     const float x5 = qr_rsq(x4);
                     x4 = qr_mul(x5, x6);
-                    x6 = qr_mul(x6, lg.a_qdr);
-                    x4 = qr_mul(x4, lg.a_lnr);
-                    x6 = qr_add(x6, lg.a_cnt);
+                    x6 = qr_mul(x6, l1.w);
+                    x4 = qr_mul(x4, l2.x);
+                    x6 = qr_add(x6, l2.y);
                     x6 = qr_add(x6, x4);
                     x4 = qr_rsq(x6);
-                    x6 = d;
-                    d = qr_mul(d, x4);
-                    d = qr_mul(d, x5);
-                    d = qr_mul(d, m.l_dff);
+                    x6 = dd;
+                    dd = qr_mul(dd, x4);
+                    dd = qr_mul(dd, x5);
+                    dd = qr_mul(dd, m2.x);
                 }
                 else
                 {
                     x6 = dot;
-                    d = 0.0f;
+                    dd = 0.0f;
                 }
 
                 bool spec_done = false;
                 float spc = 0.0f;
                 if (props & QR_PROP_SPECULAR)
                 {
-                    float x1 = ray[0], x2 = ray[1], x3 = ray[2];
-                    float a4 = qr_mul(x6, nrm[0]);
+                    float x1 = rx, x2 = ry, x3 = rz;
+                    float a4 = qr_mul(x6, nx);
                     x1 = qr_sub(x1, a4); x1 = qr_sub(x1, a4);
-                    float a5 = qr_mul(x6, nrm[1]);
+                    float a5 = qr_mul(x6, ny);
                     x2 = qr_sub(x2, a5); x2 = qr_sub(x2, a5);
-                    float a6 = qr_mul(x6, nrm[2]);
+                    float a6 = qr_mul(x6, nz);
                     x3 = qr_sub(x3, a6); x3 = qr_sub(x3, a6);
-                    a4 = lray[0]; x1 = qr_mul(x1, a4); a4 = qr_mul(a4, a4);
-                    a5 = lray[1]; x2 = qr_mul(x2, a5); a5 = qr_mul(a5, a5);
-                    a6 = lray[2]; x3 = qr_mul(x3, a6); a6 = qr_mul(a6, a6);
+                    a4 = lrx; x1 = qr_mul(x1, a4); a4 = qr_mul(a4, a4);
+                    a5 = lry; x2 = qr_mul(x2, a5); a5 = qr_mul(a5, a5);
+                    a6 = lrz; x3 = qr_mul(x3, a6); a6 = qr_mul(a6, a6);
                     a6 = qr_add(a6, a4);
                     a6 = qr_add(a6, a5);
                     x1 = qr_add(x1, x2);
@@ -901,32 +936,25 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                         spec_done = true;
                         x1 = qr_mul(x1, qr_rsq(a6));
                         x1 = qr_mul(x1, qr_rsq(r2));
-                        x1 = qr_pow_28_4(x1, m.l_pow);
-                        spc = qr_mul(x1, m.l_spc);
+                        x1 = qr_pow_28_4(x1, qr_f2u(m2.z));
+                        spc = qr_mul(x1, m2.y);
                     }
                 }
 
                 if (spec_done && !(props & QR_PROP_METAL))
                 {
                     /* LT_mtl 3090-3149 */
-                    for (int k = 0; k < 3; k++)
-                    {
-                        float x1 = qr_mul(tex[k], d);
-                        x1 = qr_mul(x1, lg.col[k]);
-                        x1 = qr_add(x1, qr_mul(lg.col[k], spc));
-                        col[k] = qr_add(x1, col[k]);
-                    }
+                    cr = qr_add(qr_add(qr_mul(qr_mul(tr, dd), l1.x), qr_mul(l1.x, spc)), cr);
+                    cg = qr_add(qr_add(qr_mul(qr_mul(tg, dd), l1.y), qr_mul(l1.y, spc)), cg);
+                    cb = qr_add(qr_add(qr_mul(qr_mul(tb, dd), l1.z), qr_mul(l1.z, spc)), cb);
                 }
                 else
                 {
                     /* LT_spc 3047-3084 */
-                    if (spec_done) d = qr_add(d, spc);
-                    for (int k = 0; k < 3; k++)
-                    {
-                        float x1 = qr_mul(tex[k], lg.col[k]);
-                        x1 = qr_mul(x1, d);
-                        col[k] = qr_add(x1, col[k]);
-                    }
+                    if (spec_done) dd = qr_add(dd, spc);
+                    cr = qr_add(qr_mul(qr_mul(tr, l1.x), dd), cr);
+                    cg = qr_add(qr_mul(qr_mul(tg, l1.y), dd), cg);
+                    cb = qr_add(qr_mul(qr_mul(tb, l1.z), dd), cb);
                 }
             }
             li = le.next;
@@ -939,90 +967,93 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
             if (!res)
             {
                 /* nothing hit: COL of this level stays 0 */
-                col[0] = col[1] = col[2] = 0.0f;
+                cr = cg = cb = 0.0f;
                 resume = -1;
             }
             else
             {
                 /* ---------------- SHADE ---------------- */
-                cur_ei = best_ei;
-                const qr_elem e = v.elems[cur_ei];
-                const qr_surface &s = v.surfs[e.simd];
+                cur_si = best_si;
+                const qr_f4 *q = v.surf + (size_t)cur_si * QR_KSURF_QUADS;
+                const qr_f4 q1 = q[1], q2 = q[2];
+                const uint32_t d = qr_f2u(q[0].w);
                 const int side = best_side;
-                l_flg = side | s.props[side];           /* FETCH_PROP */
-                const int props = l_flg;
-                const int shift = s.a_sgn[3];
-                const qr_material &m = v.mats[s.mat[side]];
+                const uint32_t props = (uint32_t)side | qr_side_props(qr_f2u(q2.w), side);   /* FETCH_PROP */
+                l_flg = (int)props;
+                const qr_f4 s0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
+                const int mi = (int)qr_f2u(side ? s0.y : s0.x);
+                const qr_f4 *mq = v.mat + (size_t)mi * QR_KMAT_QUADS;
 
-                lray[0] = ray[0]; lray[1] = ray[1]; lray[2] = ray[2];
-                hit[0] = qr_add(qr_mul(ray[0], t_buf), org[0]);
-                hit[1] = qr_add(qr_mul(ray[1], t_buf), org[1]);
-                hit[2] = qr_add(qr_mul(ray[2], t_buf), org[2]);
-                loc[0] = best_loc[0]; loc[1] = best_loc[1]; loc[2] = best_loc[2];
+                lrx = rx; lry = ry; lrz = rz;
+                hx = qr_add(qr_mul(rx, t_buf), ox);
+                hy = qr_add(qr_mul(ry, t_buf), oy);
+                hz = qr_add(qr_mul(rz, t_buf), oz);
+                lcx = blx; lcy = bly; lcz = blz;
 
-                const int kind = s.srf_t[0] == 1 ? 1 : s.srf_t[1];
-                float tex_uv[2] = {0.0f, 0.0f};
-                float nl[3] = {0.0f, 0.0f, 0.0f};       /* normal, local fields */
+                const uint32_t kind = QR_D_TAG(d) == 1 ? 1u : QR_D_KIND(d);
+                float tex_u = 0.0f, tex_v = 0.0f;
+                float n0 = 0.0f, n1 = 0.0f, n2 = 0.0f;  /* normal, local fields */
 
                 if (kind == 1)
                 {
                     /* PL_mat 4149-4193 */
                     if (props & QR_PROP_TEXTURE)
                     {
-                        tex_uv[0] = qr_sgn(loc[s.a_map[0] - shift], s.a_sgn[0]);
-                        tex_uv[1] = qr_sgn(loc[s.a_map[1] - shift], s.a_sgn[1]);
+                        tex_u = qr_sgn(qr_pick3(QR_D_MAP(d, 0), lcx, lcy, lcz), QR_D_SGN(d, 0));
+                        tex_v = qr_sgn(qr_pick3(QR_D_MAP(d, 1), lcx, lcy, lcz), QR_D_SGN(d, 1));
                     }
                     if (props & QR_PROP_NORMAL)
                     {
                         const uint32_t u = (0x3F800000u ^ (side ? 0x80000000u : 0u))
-                                         ^ (s.a_sgn[2] ? 0x80000000u : 0u);
-                        nl[s.a_map[0] - shift] = 0.0f;
-                        nl[s.a_map[1] - shift] = 0.0f;
-                        nl[s.a_map[2] - shift] = qr_u2f(u);
+                                         ^ (QR_D_SGN(d, 2) ? 0x80000000u : 0u);
+                        qr_put3(QR_D_MAP(d, 2), qr_u2f(u), n0, n1, n2);
                     }
                 }
                 else
                 if (props & QR_PROP_NORMAL)
                 {
                     /* QD_mat 4855-4899 / TP_mat 4290-4330 */
-                    float x4 = qr_mul(loc[0], s.sci[0]);
-                    float x5 = qr_mul(loc[1], s.sci[1]);
-                    float x6 = qr_mul(loc[2], s.sci[2]);
+                    float x4 = qr_mul(lcx, q1.x);
+                    float x5 = qr_mul(lcy, q1.y);
+                    float x6 = qr_mul(lcz, q1.z);
                     if (kind == 2)
                     {
-                        x4 = qr_sub(x4, s.scj[0]);
-                        x5 = qr_sub(x5, s.scj[1]);
-                        x6 = qr_sub(x6, s.scj[2]);
+                        x4 = qr_sub(x4, q2.x);
+                        x5 = qr_sub(x5, q2.y);
+                        x6 = qr_sub(x6, q2.z);
                     }
                     float x1 = qr_mul(x4, x4);
                     x1 = qr_add(x1, qr_mul(x5, x5));
                     x1 = qr_add(x1, qr_mul(x6, x6));
                     float x0 = qr_rsq(x1);
                     if (side) x0 = qr_neg(x0);
-                    nl[0] = qr_mul(x4, x0);
-                    nl[1] = qr_mul(x5, x0);
-                    nl[2] = qr_mul(x6, x0);
+                    n0 = qr_mul(x4, x0);
+                    n1 = qr_mul(x5, x0);
+                    n2 = qr_mul(x6, x0);
                 }
 
                 if (props & QR_PROP_NORMAL)
                 {
-                    if (s.a_map[3] != 0)
+                    if (QR_D_TRM(d) != 0)
                     {
                         /* MT_nrm 2184-2259: transposed matrix of the trnode */
-                        const qr_surface &t = v.surfs[s.trnode];
-                        float x4 = qr_mul(t.tci[0], nl[0]);
-                        float x5 = qr_mul(t.tcj[1], nl[1]);
-                        float x6 = qr_mul(t.tck[2], nl[2]);
+                        const qr_f4 *t = v.surf + (size_t)(int)qr_f2u(q[4].w) * QR_KSURF_QUADS;
+                        const qr_f4 t5 = t[5], t6 = t[6];
+                        const float tck_z = t[7].x;
+                        const uint32_t ttrm = QR_D_TRM(qr_f2u(t[0].w));
+                        float x4 = qr_mul(t5.x, n0);
+                        float x5 = qr_mul(t6.x, n1);
+                        float x6 = qr_mul(tck_z, n2);
                         bool renorm = true;
-                        if (t.a_map[3] != 1)
+                        if (ttrm != 1)
                         {
-                            x4 = qr_add(x4, qr_mul(t.tcj[0], nl[1]));
-                            x4 = qr_add(x4, qr_mul(t.tck[0], nl[2]));
-                            x5 = qr_add(x5, qr_mul(t.tci[1], nl[0]));
-                            x5 = qr_add(x5, qr_mul(t.tck[1], nl[2]));
-                            x6 = qr_add(x6, qr_mul(t.tci[2], nl[0]));
-                            x6 = qr_add(x6, qr_mul(t.tcj[2], nl[1]));
-                            if (t.a_map[3] == 2) renorm = false;
+                            x4 = qr_add(x4, qr_mul(t5.w, n1));
+                            x4 = qr_add(x4, qr_mul(t6.z, n2));
+                            x5 = qr_add(x5, qr_mul(t5.y, n0));
+                            x5 = qr_add(x5, qr_mul(t6.w, n2));
+                            x6 = qr_add(x6, qr_mul(t5.z, n0));
+                            x6 = qr_add(x6, qr_mul(t6.y, n1));
+                            if (ttrm == 2) renorm = false;
                         }
                         if (renorm)
                         {
@@ -1032,46 +1063,49 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                             const float x0 = qr_rsq(x1);
                             x4 = qr_mul(x4, x0); x5 = qr_mul(x5, x0); x6 = qr_mul(x6, x0);
                         }
-                        nrm[0] = x4; nrm[1] = x5; nrm[2] = x6;
+                        nx = x4; ny = x5; nz = x6;
                     }
                     else
                     {
-                        nrm[0] = nl[0]; nrm[1] = nl[1]; nrm[2] = nl[2];
+                        nx = n0; ny = n1; nz = n2;
                     }
                 }
 
                 /* MT_mat 2286-2327: texel */
+                const qr_f4 m1 = mq[1], m4 = mq[4];
                 uint32_t p = 0;
                 if (props & QR_PROP_TEXTURE)
                 {
-                    float tx = tex_uv[m.t_map[0]];
-                    float ty = tex_uv[m.t_map[1]];
-                    tx = qr_sub(tx, m.xoffs);
-                    ty = qr_sub(ty, m.yoffs);
-                    tx = qr_mul(tx, m.xscal);
-                    ty = qr_mul(ty, m.yscal);
-                    const uint32_t ix = (uint32_t)qr_cvm(tx) & m.xmask;
-                    const uint32_t iy = ((uint32_t)qr_cvm(ty) & m.ymask) << m.yshft;
+                    const qr_f4 m0 = mq[0];
+                    const uint32_t ys = qr_f2u(m1.z);
+                    float tx = (ys & 0x100u) ? tex_v : tex_u;
+                    float ty = (ys & 0x200u) ? tex_v : tex_u;
+                    tx = qr_sub(tx, m0.z);
+                    ty = qr_sub(ty, m0.w);
+                    tx = qr_mul(tx, m0.x);
+                    ty = qr_mul(ty, m0.y);
+                    const uint32_t ix = (uint32_t)qr_cvm(tx) & qr_f2u(m1.x);
+                    const uint32_t iy = ((uint32_t)qr_cvm(ty) & qr_f2u(m1.y)) << (ys & 0xFFu);
                     p = ix + iy;
                 }
-                const uint32_t texel = v.texels[m.tex + p];
-                tex[0] = qr_unpack(texel, 16, m, props);
-                tex[1] = qr_unpack(texel, 8, m, props);
-                tex[2] = qr_unpack(texel, 0, m, props);
+                const uint32_t texel = v.texels[(int)qr_f2u(m1.w) + p];
+                tr = qr_unpack(texel, 16, qr_f2u(m4.z), m4.y, props);
+                tg = qr_unpack(texel, 8, qr_f2u(m4.z), m4.y, props);
+                tb = qr_unpack(texel, 0, qr_f2u(m4.z), m4.y, props);
 
                 if (props & QR_PROP_LIGHT)
                 {
                     /* LT_set 3164-3177 */
-                    col[0] = tex[0]; col[1] = tex[1]; col[2] = tex[2];
+                    cr = tr; cg = tg; cb = tb;
                     li = QR_NIL;
                 }
                 else
                 {
                     /* ambient 2721-2756 */
-                    col[0] = qr_mul(tex[0], h.amb[0]);
-                    col[1] = qr_mul(tex[1], h.amb[1]);
-                    col[2] = qr_mul(tex[2], h.amb[2]);
-                    li = s.lst_lgt[side];
+                    cr = qr_mul(tr, h.amb[0]);
+                    cg = qr_mul(tg, h.amb[1]);
+                    cb = qr_mul(tb, h.amb[2]);
+                    li = (int)qr_f2u(side ? s0.w : s0.z);
                 }
                 lights_phase = true;
             }
@@ -1084,25 +1118,25 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
             while (li != QR_NIL)
             {
                 const qr_elem le = v.elems[li];
-                const qr_light &lg = v.lgts[le.simd];
-                float x1 = qr_sub(lg.pos[0], hit[0]);
-                float x2 = qr_sub(lg.pos[1], hit[1]);
-                float x3 = qr_sub(lg.pos[2], hit[2]);
-                float d = qr_mul(x1, nrm[0]);
-                d = qr_add(d, qr_mul(x2, nrm[1]));
-                d = qr_add(d, qr_mul(x3, nrm[2]));
-                if (0.0f < d)
+                const qr_f4 l0 = v.lgt[(size_t)le.simd * QR_KLGT_QUADS];
+                const float x1 = qr_sub(l0.x, hx);
+                const float x2 = qr_sub(l0.y, hy);
+                const float x3 = qr_sub(l0.z, hz);
+                float dd = qr_mul(x1, nx);
+                dd = qr_add(dd, qr_mul(x2, ny));
+                dd = qr_add(dd, qr_mul(x3, nz));
+                if (0.0f < dd)
                 {
-                    dot = d;
-                    org[0] = hit[0]; org[1] = hit[1]; org[2] = hit[2];
-                    ray[0] = x1; ray[1] = x2; ray[2] = x3;
+                    dot = dd;
+                    ox = hx; oy = hy; oz = hz;
+                    rx = x1; ry = x2; rz = x3;
                     t_min = 0.0f;
-                    t_max = lg.t_max;
+                    t_max = l0.w;
                     head = le.data_p;
                     mode = QR_MODE_SHADOW;
-                    p_obj = v.elems[cur_ei].simd;
+                    p_obj = cur_si;
                     p_flg = l_flg | QR_FLAG_PASS_BACK | QR_FLAG_SHAD;
-                    if (cnt) cnt->shadow++;
+                    cnt.shadow++;
                     go_shadow = true;
                     break;
                 }
@@ -1113,59 +1147,57 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
         }
 
         /* ------------- TRANSPARENCY / REFLECTION / unwinding ------------- */
+        bool walk_again = false;
         for (;;)
         {
-            const qr_surface *sp = 0;
-            const qr_material *mp = 0;
-            int props = 0, side = 0;
-
             if (resume == -1)
             {
-                /* return colour "col" of the finished level to its parent */
-                if (lvl == 0) goto done;
+                /* return colour of the finished level to its parent */
+                if (lvl == 0) break;
                 lvl--;
                 const qr_frame &f = stack[lvl];
-                const float cc[3] = { col[0], col[1], col[2] };
-                col[0] = f.col[0]; col[1] = f.col[1]; col[2] = f.col[2];
-                lray[0] = f.ray[0]; lray[1] = f.ray[1]; lray[2] = f.ray[2];
-                hit[0] = f.hit[0]; hit[1] = f.hit[1]; hit[2] = f.hit[2];
-                nrm[0] = f.nrm[0]; nrm[1] = f.nrm[1]; nrm[2] = f.nrm[2];
-                loc[0] = f.loc[0]; loc[1] = f.loc[1]; loc[2] = f.loc[2];
+                const float ccr = cr, ccg = cg, ccb = cb;
+                cr = f.col[0]; cg = f.col[1]; cb = f.col[2];
+                lrx = f.ray[0]; lry = f.ray[1]; lrz = f.ray[2];
+                hx = f.hit[0]; hy = f.hit[1]; hz = f.hit[2];
+                nx = f.nrm[0]; ny = f.nrm[1]; nz = f.nrm[2];
+                lcx = f.loc[0]; lcy = f.loc[1]; lcz = f.loc[2];
                 c_trn = f.c_trn; c_rfl = f.c_rfl;
-                cur_ei = f.ei; l_flg = f.flg;
+                cur_si = f.si; l_flg = f.flg;
                 if (f.stage == 0)
                 {
                     /* TR_ret 3534-3552 */
-                    xr[0] = qr_mul(cc[0], c_trn);
-                    xr[1] = qr_mul(cc[1], c_trn);
-                    xr[2] = qr_mul(cc[2], c_trn);
+                    xr = qr_mul(ccr, c_trn); xg = qr_mul(ccg, c_trn); xb = qr_mul(ccb, c_trn);
                     resume = 1;
                 }
                 else
                 {
                     /* RF_ret 3868-3884 */
-                    xr[0] = qr_mul(cc[0], c_rfl);
-                    xr[1] = qr_mul(cc[1], c_rfl);
-                    xr[2] = qr_mul(cc[2], c_rfl);
+                    xr = qr_mul(ccr, c_rfl); xg = qr_mul(ccg, c_rfl); xb = qr_mul(ccb, c_rfl);
                     resume = 2;
                 }
             }
 
-            sp = &v.surfs[v.elems[cur_ei].simd];
-            side = l_flg & 1;
-            props = l_flg;
-            mp = &v.mats[sp->mat[side]];
-            const qr_surface &s = *sp;
-            const qr_material &m = *mp;
+            const int side = l_flg & 1;
+            const uint32_t props = (uint32_t)l_flg;
+            const qr_f4 s0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
+            const qr_f4 s1 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS + 1];
+            const int mi = (int)qr_f2u(side ? s0.y : s0.x);
+            const qr_f4 *mq = v.mat + (size_t)mi * QR_KMAT_QUADS;
+            const qr_f4 m3 = mq[3];
+            const float m_c_rfl = mq[2].w;
+            const float m_c_trn = m3.x, m_c_rfr = m3.y, m_rfr_2 = m3.z, m_c_rcp = m3.w;
+
+            bool push = false;
+            int  push_stage = 0, push_head = QR_NIL, push_flg = 0;
+            float nwx = 0.0f, nwy = 0.0f, nwz = 0.0f;
 
             if (resume == 0)
             {
                 /* TRANSPARENCY 3185-3532 */
-                c_trn = m.c_trn;
-                c_rfl = m.c_rfl;
-                xr[0] = xr[1] = xr[2] = 0.0f;
-                bool push = false;
-                float nw[3] = {0.0f, 0.0f, 0.0f};
+                c_trn = m_c_trn;
+                c_rfl = m_c_rfl;
+                xr = xg = xb = 0.0f;
 
                 if (!(props & QR_PROP_OPAQUE))
                 {
@@ -1173,17 +1205,17 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                     float x0 = 0.0f, x4 = 0.0f, x7 = 0.0f;
                     if ((props & QR_PROP_REFRACT) || (props & QR_PROP_FRESNEL))
                     {
-                        float a[3];
-                        x4 = qr_norm_dot(lray, nrm, a);
-                        x0 = qr_mul(x4, m.c_rfr);
+                        float ax, ay, az;
+                        x4 = qr_norm_dot(lrx, lry, lrz, nx, ny, nz, ax, ay, az);
+                        x0 = qr_mul(x4, m_c_rfr);
                         x7 = qr_mul(x0, x0);
                         x7 = qr_add(x7, 1.0f);
-                        x7 = qr_sub(x7, m.rfr_2);
+                        x7 = qr_sub(x7, m_rfr_2);
                         if ((props & QR_PROP_FRESNEL) && !(0.0f <= x7))
                         {
                             /* TR_tir 3280-3295 */
                             c_trn = 0.0f;
-                            c_rfl = qr_add(m.c_rfl, m.c_trn);
+                            c_rfl = qr_add(m_c_rfl, m_c_trn);
                             go = false;
                         }
                         if (go)
@@ -1192,68 +1224,49 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                             x0 = qr_add(x0, x7);
                             if (props & QR_PROP_REFRACT)
                             {
-                                nw[0] = qr_sub(qr_mul(a[0], m.c_rfr), qr_mul(nrm[0], x0));
-                                nw[1] = qr_sub(qr_mul(a[1], m.c_rfr), qr_mul(nrm[1], x0));
-                                nw[2] = qr_sub(qr_mul(a[2], m.c_rfr), qr_mul(nrm[2], x0));
+                                nwx = qr_sub(qr_mul(ax, m_c_rfr), qr_mul(nx, x0));
+                                nwy = qr_sub(qr_mul(ay, m_c_rfr), qr_mul(ny, x0));
+                                nwz = qr_sub(qr_mul(az, m_c_rfr), qr_mul(nz, x0));
                             }
                             else
                             {
-                                nw[0] = lray[0]; nw[1] = lray[1]; nw[2] = lray[2];
+                                nwx = lrx; nwy = lry; nwz = lrz;
                             }
                         }
                     }
                     else
                     {
-                        nw[0] = lray[0]; nw[1] = lray[1]; nw[2] = lray[2];
+                        nwx = lrx; nwy = lry; nwz = lrz;
                     }
                     if (go && (props & QR_PROP_FRESNEL))
                     {
                         /* TR_ini 3385-3424 */
-                        float a0 = qr_fresnel(x4, m.c_rfr, x0, x7);
-                        a0 = qr_mul(a0, m.c_trn);
-                        c_trn = qr_sub(m.c_trn, a0);
-                        c_rfl = qr_add(m.c_rfl, a0);
+                        float a0 = qr_fresnel(x4, m_c_rfr, x0, x7);
+                        a0 = qr_mul(a0, m_c_trn);
+                        c_trn = qr_sub(m_c_trn, a0);
+                        c_rfl = qr_add(m_c_rfl, a0);
                     }
                     if (go && lvl < h.depth)
                     {
                         push = true;
+                        push_stage = 0;
+                        push_head = (int)qr_f2u(side ? s1.x : s1.y);    /* FETCH_IPTR */
+                        push_flg = l_flg | QR_FLAG_PASS_THRU;
+                        cnt.refract++;
                     }
                 }
-
-                if (push)
-                {
-                    qr_frame &f = stack[lvl];
-                    f.col[0] = col[0]; f.col[1] = col[1]; f.col[2] = col[2];
-                    f.ray[0] = lray[0]; f.ray[1] = lray[1]; f.ray[2] = lray[2];
-                    f.hit[0] = hit[0]; f.hit[1] = hit[1]; f.hit[2] = hit[2];
-                    f.nrm[0] = nrm[0]; f.nrm[1] = nrm[1]; f.nrm[2] = nrm[2];
-                    f.loc[0] = loc[0]; f.loc[1] = loc[1]; f.loc[2] = loc[2];
-                    f.c_trn = c_trn; f.c_rfl = c_rfl;
-                    f.ei = cur_ei; f.flg = l_flg; f.stage = 0;
-                    org[0] = hit[0]; org[1] = hit[1]; org[2] = hit[2];
-                    ray[0] = nw[0]; ray[1] = nw[1]; ray[2] = nw[2];
-                    t_min = 0.0f;
-                    t_max = h.cam_t_max;
-                    head = s.lst_srf[side ^ 1];         /* FETCH_IPTR */
-                    mode = QR_MODE_CLOSEST;
-                    p_obj = v.elems[cur_ei].simd;
-                    p_flg = l_flg | QR_FLAG_PASS_THRU;
-                    lvl++;
-                    if (cnt) cnt->refract++;
-                    break;
-                }
-                resume = 1;
+                if (!push) resume = 1;
             }
 
             if (resume == 1)
             {
                 /* TR_mix 3564-3598 */
-                float x0 = qr_sub(1.0f, m.c_trn);
-                x0 = qr_sub(x0, m.c_rfl);
+                float x0 = qr_sub(1.0f, m_c_trn);
+                x0 = qr_sub(x0, m_c_rfl);
                 if (!(0.0f <= x0)) x0 = 0.0f;
-                col[0] = qr_add(xr[0], qr_mul(col[0], x0));
-                col[1] = qr_add(xr[1], qr_mul(col[1], x0));
-                col[2] = qr_add(xr[2], qr_mul(col[2], x0));
+                cr = qr_add(xr, qr_mul(cr, x0));
+                cg = qr_add(xg, qr_mul(cg, x0));
+                cb = qr_add(xb, qr_mul(cb, x0));
 
                 /* REFLECTIONS 3604-3866 */
                 bool go = (props & QR_PROP_REFLECT) != 0;
@@ -1264,26 +1277,26 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                     continue;
                 }
 
-                float a[3], nw[3];
-                const float d = qr_norm_dot(lray, nrm, a);
-                for (int k = 0; k < 3; k++)
+                float ax, ay, az;
+                const float dd = qr_norm_dot(lrx, lry, lrz, nx, ny, nz, ax, ay, az);
                 {
-                    const float nd = qr_mul(nrm[k], d);
-                    nw[k] = qr_sub(qr_sub(a[k], nd), nd);
+                    float nd = qr_mul(nx, dd); nwx = qr_sub(qr_sub(ax, nd), nd);
+                    nd = qr_mul(ny, dd);       nwy = qr_sub(qr_sub(ay, nd), nd);
+                    nd = qr_mul(nz, dd);       nwz = qr_sub(qr_sub(az, nd), nd);
                 }
 
                 if ((props & QR_PROP_FRESNEL) && (props & QR_PROP_OPAQUE))
                 {
-                    float a0 = d;
+                    float a0 = dd;
                     if (props & QR_PROP_METAL)
                     {
                         /* 3729-3751 */
-                        float a6 = m.c_rcp;
+                        float a6 = m_c_rcp;
                         float a4 = qr_mul(a0, a6);
                         a4 = qr_add(a4, a4);
                         a0 = qr_mul(a0, a0);
                         a6 = qr_mul(a6, a6);
-                        a6 = qr_add(a6, m.ext_2);
+                        a6 = qr_add(a6, mq[4].x);
                         float a1 = qr_mul(a0, a6);
                         a0 = qr_add(a0, a6);
                         a1 = qr_add(a1, 1.0f);
@@ -1298,63 +1311,72 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                     else
                     {
                         /* RF_mtl 3767-3796 */
-                        float y0 = qr_mul(a0, m.c_rfr);
+                        float y0 = qr_mul(a0, m_c_rfr);
                         float y7 = qr_mul(y0, y0);
                         y7 = qr_add(y7, 1.0f);
-                        y7 = qr_sub(y7, m.rfr_2);
+                        y7 = qr_sub(y7, m_rfr_2);
                         y7 = qr_sqrt(y7);
                         y0 = qr_add(y0, y7);
-                        a0 = qr_fresnel(a0, m.c_rfr, y0, y7);
+                        a0 = qr_fresnel(a0, m_c_rfr, y0, y7);
                     }
                     /* RF_pre 3806-3815 */
                     a0 = qr_sub(a0, 1.0f);
-                    a0 = qr_mul(a0, m.c_rfl);
-                    c_rfl = qr_add(m.c_rfl, a0);
+                    a0 = qr_mul(a0, m_c_rfl);
+                    c_rfl = qr_add(m_c_rfl, a0);
                 }
 
-                xr[0] = xr[1] = xr[2] = 0.0f;
+                xr = xg = xb = 0.0f;
                 if (lvl < h.depth)
                 {
-                    qr_frame &f = stack[lvl];
-                    f.col[0] = col[0]; f.col[1] = col[1]; f.col[2] = col[2];
-                    f.ray[0] = lray[0]; f.ray[1] = lray[1]; f.ray[2] = lray[2];
-                    f.hit[0] = hit[0]; f.hit[1] = hit[1]; f.hit[2] = hit[2];
-                    f.nrm[0] = nrm[0]; f.nrm[1] = nrm[1]; f.nrm[2] = nrm[2];
-                    f.loc[0] = loc[0]; f.loc[1] = loc[1]; f.loc[2] = loc[2];
-                    f.c_trn = c_trn; f.c_rfl = c_rfl;
-                    f.ei = cur_ei; f.flg = l_flg; f.stage = 1;
-                    org[0] = hit[0]; org[1] = hit[1]; org[2] = hit[2];
-                    ray[0] = nw[0]; ray[1] = nw[1]; ray[2] = nw[2];
-                    t_min = 0.0f;
-                    t_max = h.cam_t_max;
-                    head = s.lst_srf[side];             /* FETCH_XPTR */
-                    mode = QR_MODE_CLOSEST;
-                    p_obj = v.elems[cur_ei].simd;
-                    p_flg = l_flg | QR_FLAG_PASS_BACK;
-                    lvl++;
-                    if (cnt) cnt->reflect++;
-                    break;
+                    push = true;
+                    push_stage = 1;
+                    push_head = (int)qr_f2u(side ? s1.y : s1.x);        /* FETCH_XPTR */
+                    push_flg = l_flg | QR_FLAG_PASS_BACK;
+                    cnt.reflect++;
                 }
-                resume = 2;
+                else
+                {
+                    resume = 2;
+                }
+            }
+
+            if (push)
+            {
+                qr_frame &f = stack[lvl];
+                f.col[0] = cr; f.col[1] = cg; f.col[2] = cb;
+                f.ray[0] = lrx; f.ray[1] = lry; f.ray[2] = lrz;
+                f.hit[0] = hx; f.hit[1] = hy; f.hit[2] = hz;
+                f.nrm[0] = nx; f.nrm[1] = ny; f.nrm[2] = nz;
+                f.loc[0] = lcx; f.loc[1] = lcy; f.loc[2] = lcz;
+                f.c_trn = c_trn; f.c_rfl = c_rfl;
+                f.si = cur_si; f.flg = l_flg; f.stage = push_stage;
+                ox = hx; oy = hy; oz = hz;
+                rx = nwx; ry = nwy; rz = nwz;
+                t_min = 0.0f;
+                t_max = h.cam_t_max;
+                head = push_head;
+                mode = QR_MODE_CLOSEST;
+                p_obj = cur_si;
+                p_flg = push_flg;
+                lvl++;
+                walk_again = true;
+                break;
             }
 
             if (resume == 2)
             {
                 /* RF_mix 3888-3908 */
-                col[0] = qr_add(xr[0], col[0]);
-                col[1] = qr_add(xr[1], col[1]);
-                col[2] = qr_add(xr[2], col[2]);
+                cr = qr_add(xr, cr);
+                cg = qr_add(xg, cg);
+                cb = qr_add(xb, cb);
                 resume = -1;
-                continue;
             }
         }
+        if (!walk_again) break;
     }
 
-done:
-    out_col[0] = col[0];
-    out_col[1] = col[1];
-    out_col[2] = col[2];
-    *out_t = primary_t;
+    out_r = cr; out_g = cg; out_b = cb;
+    out_t = primary_t;
 }
 
 /* ---- epilogue helpers, XX_end 5221-5343 / FRAME_SIMD 988-1006 -------------- */
@@ -1366,17 +1388,14 @@ QR_HD float qr_clamp1(float c)                  /* minps: source on NaN */
 
 QR_HD uint32_t qr_pack(const qr_blob_header &h, float r, float g, float b)
 {
-    float c[3] = { r, g, b };
-    uint32_t pix = 0;
-    for (int k = 0; k < 3; k++)
-    {
-        float x = c[k];
-        if (h.ctx_flags & QR_PROP_GAMMA) x = qr_sqrt(x);
-        x = qr_mul(x, h.cam_clamp);
-        const uint32_t iv = (uint32_t)qr_cvn(x) & h.cam_cmask;
-        pix |= iv << (k == 0 ? 16 : k == 1 ? 8 : 0);
-    }
-    return pix;
+    const bool gamma = (h.ctx_flags & QR_PROP_GAMMA) != 0;
+    const float clampv = h.cam_clamp;
+    const uint32_t cmask = h.cam_cmask;
+    if (gamma) { r = qr_sqrt(r); g = qr_sqrt(g); b = qr_sqrt(b); }
+    const uint32_t ir = (uint32_t)qr_cvn(qr_mul(r, clampv)) & cmask;
+    const uint32_t ig = (uint32_t)qr_cvn(qr_mul(g, clampv)) & cmask;
+    const uint32_t ib = (uint32_t)qr_cvn(qr_mul(b, clampv)) & cmask;
+    return (ir << 16) | (ig << 8) | ib;
 }
 
 #endif /* QR_CORE_CUH */
