@@ -21,6 +21,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
 #include <new>
@@ -28,9 +29,16 @@
 #include "quadray_b200.h"
 #include "qr_core.cuh"
 
-#define QR_CTA_THREADS 256
-#define QR_WARPS       (QR_CTA_THREADS / 32)
-#define QR_CTAS_PER_SM 2            /* register budget: 128 per thread */
+/*
+ * Launch shapes (threads per CTA, resident CTAs per SM the register budget is
+ * sized for).  One CTA stages one copy of the scene prefix, so a few large
+ * CTAs leave more of the 256 KB L1/shared array to the L1 cache than many
+ * small ones.  QR_B200_SHAPE=<index> overrides the default (tuning only).
+ */
+struct qr_shape { int threads, ctas; };
+static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {384, 1}, {128, 4} };
+#define QR_N_SHAPES     6
+#define QR_DEFAULT_SHAPE 0
 
 /* ------------------------------------------------------------------ PTX --- */
 
@@ -94,15 +102,35 @@ extern __shared__ __align__(128) uint8_t qr_smem[];
  * is derived from the qr_smem symbol, so the compiler emits LDS.128.
  * STAGED = false (prefix larger than shared memory): everything through L1/L2.
  */
-template <bool STAGED>
-__global__ void __launch_bounds__(QR_CTA_THREADS, QR_CTAS_PER_SM)
+/* staged view: hot sections addressed in the shared window, the rest in global memory */
+__device__ __forceinline__ void qr_view_setup(qr_view<true> &v, const uint8_t *img)
+{
+    const qr_blob_header *h = (const qr_blob_header *)qr_smem;
+    const uint32_t base = smem_u32(qr_smem);
+    v.h      = h;
+    v.surf   = base + h->off_surf;
+    v.shade  = base + (uint32_t)h->pad3[0];
+    v.mat    = base + h->off_mat;
+    v.lgt    = base + h->off_lgt;
+    v.elems  = (const qr_kelem *)(img + h->off_elem);
+    v.tiles  = (const int32_t *)(img + h->off_tiles);
+    v.texels = (const uint32_t *)(img + h->off_texels);
+}
+
+__device__ __forceinline__ void qr_view_setup(qr_view<false> &v, const uint8_t *img)
+{
+    qr_view_init(v, img);
+}
+
+template <bool STAGED, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS)
 qr_render_kernel(const qr_launch p)
 {
     __shared__ __align__(8) uint64_t bar;
 
     const int lane = threadIdx.x & 31;
 
-    qr_view v;
+    qr_view<STAGED> v;
     if (STAGED)
     {
         /* one elected thread issues the TMA bulk copies, all wait on the mbarrier */
@@ -126,12 +154,8 @@ qr_render_kernel(const qr_launch p)
             }
         }
         mbar_wait(&bar, 0);
-        qr_view_init(v, qr_smem, p.blob);
     }
-    else
-    {
-        qr_view_init(v, p.blob, p.blob);
-    }
+    qr_view_setup(v, p.blob);
 
     const qr_blob_header &h = *v.h;
     const int fsaa  = h.fsaa;
@@ -180,7 +204,7 @@ qr_render_kernel(const qr_launch p)
             const bool live = px < x_res;
             if (live)
             {
-                qr_trace_sample(v, px, y, lane4, stack, col[0], col[1], col[2], t, cnt);
+                qr_trace_sample<STAGED>(v, px, y, lane4, stack, col[0], col[1], col[2], t, cnt);
                 n_primary++;
                 if (p.t_out != NULL)
                 {
@@ -278,6 +302,21 @@ qr_fp32_peak_kernel(float *out, float a, float b, int iters)
 
 /* ------------------------------------------------------------ host side --- */
 
+typedef void (*qr_kernel_fn)(const qr_launch);
+
+static qr_kernel_fn qr_kernel_of(bool staged, int shape)
+{
+    switch (shape)
+    {
+        case 1:  return staged ? qr_render_kernel<true, 512, 1> : qr_render_kernel<false, 512, 1>;
+        case 2:  return staged ? qr_render_kernel<true, 640, 1> : qr_render_kernel<false, 640, 1>;
+        case 3:  return staged ? qr_render_kernel<true, 768, 1> : qr_render_kernel<false, 768, 1>;
+        case 4:  return staged ? qr_render_kernel<true, 384, 1> : qr_render_kernel<false, 384, 1>;
+        case 5:  return staged ? qr_render_kernel<true, 128, 4> : qr_render_kernel<false, 128, 4>;
+        default: return staged ? qr_render_kernel<true, 256, 2> : qr_render_kernel<false, 256, 2>;
+    }
+}
+
 #define QR_MAX_DEV 16
 
 struct qr_dev
@@ -308,6 +347,7 @@ struct qr_ctx
     uint32_t        stage_bytes;
     uint64_t        launches;
     uint64_t        rays[4];
+    int             shape;          /* index into g_shapes */
     cudaFuncAttributes fattr;
     char            err[512];
 };
@@ -426,8 +466,16 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         }
     }
 
+    ctx->shape = QR_DEFAULT_SHAPE;
+    {
+        const char *env = getenv("QR_B200_SHAPE");
+        if (env != NULL && env[0] >= '0' && env[0] < '0' + QR_N_SHAPES && env[1] == 0)
+        {
+            ctx->shape = env[0] - '0';
+        }
+    }
     cudaSetDevice(ctx->dev[0].id);
-    e = cudaFuncGetAttributes(&ctx->fattr, qr_render_kernel<true>);
+    e = cudaFuncGetAttributes(&ctx->fattr, (const void *)qr_kernel_of(true, ctx->shape));
     if (e != cudaSuccess)
     {
         int rc = qr_fail(NULL, QR_E_CUDA, "qr_init: kernel image not loadable on device %d: %s",
@@ -555,7 +603,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     {
         return rc;
     }
-    qr_kscene_pack(blob, d0.blob_h);
+    if (qr_kscene_pack(blob, d0.blob_h) != 0)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob: surface list is not well nested");
+    }
     const qr_blob_header *kh = (const qr_blob_header *)d0.blob_h;
 
     for (int i = 0; i < ctx->ndev; i++)
@@ -590,18 +641,14 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         qr_dev &d = ctx->dev[i];
         int nb = 0;
         QR_CUDA(ctx, cudaSetDevice(d.id));
+        const void *fn = (const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape);
         if (ctx->stage_bytes != 0)
         {
-            QR_CUDA(ctx, cudaFuncSetAttribute(qr_render_kernel<true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stage_bytes));
-            QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel<true>,
-                         QR_CTA_THREADS, ctx->stage_bytes));
+            QR_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)ctx->stage_bytes));
         }
-        else
-        {
-            QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, qr_render_kernel<false>,
-                         QR_CTA_THREADS, 0));
-        }
+        QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn,
+                     g_shapes[ctx->shape].threads, ctx->stage_bytes));
         if (nb < 1)
         {
             return qr_fail(ctx, QR_E_CUDA, "kernel does not fit on device %d", d.id);
@@ -635,20 +682,17 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
 
     const unsigned int n_items = (unsigned int)(ty1 - ty0) * ctx->hdr.tls_row * ctx->hdr.tile_h;
     unsigned int grid = (unsigned int)(d.sm_count * d.ctas_per_sm);
-    const unsigned int need = (n_items + QR_WARPS - 1) / QR_WARPS;
+    const int threads = g_shapes[ctx->shape].threads;
+    const unsigned int warps = (unsigned int)threads / 32u;
+    const unsigned int need = (n_items + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
 
     QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
     QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
-    if (ctx->stage_bytes != 0)
-    {
-        qr_render_kernel<true><<<grid, QR_CTA_THREADS, ctx->stage_bytes, d.stream>>>(p);
-    }
-    else
-    {
-        qr_render_kernel<false><<<grid, QR_CTA_THREADS, 0, d.stream>>>(p);
-    }
+    void *args[] = { (void *)&p };
+    QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
+                                  dim3(grid), dim3(threads), args, ctx->stage_bytes, d.stream));
     QR_CUDA(ctx, cudaGetLastError());
     QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     d.timed = true;
@@ -949,7 +993,7 @@ extern "C" int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info)
         return QR_E_ARG;
     }
     info->sm_count = ctx->dev[0].sm_count;
-    info->threads_per_cta = QR_CTA_THREADS;
+    info->threads_per_cta = g_shapes[ctx->shape].threads;
     info->ctas_per_sm = ctx->dev[0].ctas_per_sm;
     info->regs_per_thread = ctx->fattr.numRegs;
     info->local_bytes_per_thread = (int)ctx->fattr.localSizeBytes;

@@ -110,31 +110,72 @@ QR_HD bool qr_ge(float a, float b) { return !(a <  b); }    /* cge = NLT */
 
 /* ---- scene view (packed image, qr_kscene.h) -------------------------------- */
 
+/*
+ * SH = true : the kscene prefix sits in shared memory; bases are 32-bit
+ *             shared-window addresses and quads are read with ld.shared.v4
+ *             (one LDS.128, address = register + immediate)
+ * SH = false: bases are byte pointers (global memory on the device, plain
+ *             memory in the host build)
+ */
+template <bool SH> struct qr_hot;
+
+template <> struct qr_hot<false>
+{
+    typedef const uint8_t *base_t;
+#if defined(__CUDACC__)
+    static __host__ __device__ __forceinline__ qr_f4 ld(base_t b, uint32_t off)
+#else
+    static inline qr_f4 ld(base_t b, uint32_t off)
+#endif
+    {
+        return *(const qr_f4 *)(b + off);
+    }
+};
+
+#if defined(__CUDACC__)
+template <> struct qr_hot<true>
+{
+    typedef uint32_t base_t;
+    static __device__ __forceinline__ qr_f4 ld(base_t b, uint32_t off)
+    {
+        qr_f4 r;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+            : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(b + off));
+        return r;
+    }
+};
+#endif
+
+template <bool SH>
 struct qr_view
 {
     const qr_blob_header *h;
-    const qr_f4          *surf;     /* QR_KSURF_QUADS per surface */
-    const qr_f4          *shade;    /* QR_KSHADE_QUADS per surface */
-    const qr_f4          *mat;      /* QR_KMAT_QUADS per material */
-    const qr_f4          *lgt;      /* QR_KLGT_QUADS per light */
-    const qr_elem        *elems;
+    typename qr_hot<SH>::base_t surf;   /* QR_KSURF_QUADS per surface */
+    typename qr_hot<SH>::base_t shade;  /* QR_KSHADE_QUADS per surface */
+    typename qr_hot<SH>::base_t mat;    /* QR_KMAT_QUADS per material */
+    typename qr_hot<SH>::base_t lgt;    /* QR_KLGT_QUADS per light */
+    const qr_kelem       *elems;
     const int32_t        *tiles;
     const uint32_t       *texels;
 };
 
-/* "hot" = header + surfaces + shading records + materials + lights (the
- * kscene prefix, possibly a shared-memory copy), "cold" = the whole image */
-QR_HD void qr_view_init(qr_view &v, const void *hot, const void *cold)
+/* quad "q" of record "i" of a section with "quads" quads per record */
+#define QR_SURF(v, i, q)  qr_hot<SH>::ld((v).surf,  (uint32_t)(i) * (QR_KSURF_QUADS * 16u) + (q) * 16u)
+#define QR_SHADE(v, i, q) qr_hot<SH>::ld((v).shade, (uint32_t)(i) * (QR_KSHADE_QUADS * 16u) + (q) * 16u)
+#define QR_MAT(v, i, q)   qr_hot<SH>::ld((v).mat,   (uint32_t)(i) * (QR_KMAT_QUADS * 16u) + (q) * 16u)
+#define QR_LGT(v, i, q)   qr_hot<SH>::ld((v).lgt,   (uint32_t)(i) * (QR_KLGT_QUADS * 16u) + (q) * 16u)
+
+/* host / global-memory view: "img" is the whole kscene image */
+QR_HD void qr_view_init(qr_view<false> &v, const void *img)
 {
-    const uint8_t *a = (const uint8_t *)hot;
-    const uint8_t *b = (const uint8_t *)cold;
-    const qr_blob_header *h = (const qr_blob_header *)hot;
+    const uint8_t *b = (const uint8_t *)img;
+    const qr_blob_header *h = (const qr_blob_header *)img;
     v.h      = h;
-    v.surf   = (const qr_f4 *)(a + h->off_surf);
-    v.shade  = (const qr_f4 *)(a + (uint32_t)h->pad3[0]);
-    v.mat    = (const qr_f4 *)(a + h->off_mat);
-    v.lgt    = (const qr_f4 *)(a + h->off_lgt);
-    v.elems  = (const qr_elem *)(b + h->off_elem);
+    v.surf   = b + h->off_surf;
+    v.shade  = b + (uint32_t)h->pad3[0];
+    v.mat    = b + h->off_mat;
+    v.lgt    = b + h->off_lgt;
+    v.elems  = (const qr_kelem *)(b + h->off_elem);
     v.tiles  = (const int32_t *)(b + h->off_tiles);
     v.texels = (const uint32_t *)(b + h->off_texels);
 }
@@ -178,11 +219,9 @@ QR_HD void qr_put3(uint32_t i, float v, float &a0, float &a1, float &a2)
  * products first, then the off-diagonal terms of each row in column order;
  * a_map[L] == 1 keeps the diagonal only (scaling fast path).
  */
-QR_HD void qr_xform(const qr_f4 *q, uint32_t trm, float v1, float v2, float v3,
-                    float &o4, float &o5, float &o6)
+QR_HD void qr_xform(const qr_f4 q5, const qr_f4 q6, const float tck_z, uint32_t trm,
+                    float v1, float v2, float v3, float &o4, float &o5, float &o6)
 {
-    const qr_f4 q5 = q[5], q6 = q[6];
-    const float tck_z = q[7].x;
     float x4 = qr_mul(q5.x, v1);
     float x5 = qr_mul(q6.x, v2);
     float x6 = qr_mul(tck_z, v3);
@@ -198,22 +237,14 @@ QR_HD void qr_xform(const qr_f4 *q, uint32_t trm, float v1, float v2, float v3,
     o4 = x4; o5 = x5; o6 = x6;
 }
 
-/* per-walk transform-caching state (ctx DFF / RAY_IJK / LOCAL(OBJ)) */
-struct qr_walk_state
-{
-    float dx, dy, dz;        /* DFF_X/Y/Z */
-    float di, dj, dk;        /* DFF_I/J/K */
-    float ri, rj, rk;        /* RAY_I/J/K */
-    int   l_obj;             /* ctx_LOCAL(OBJ): trnode's last element */
-};
-
 /*
- * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of a surface whose
- * quads start at "q" (descriptor "d").  (lrx, ldx) are the ray / diff in the
+ * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of surface "si"
+ * (descriptor "d", first quad "q0").  (lr, ld) are the ray / diff in the
  * surface's field set (world or trnode space).  On success lx/ly/lz hold the
  * (possibly adjusted) local hit point.
  */
-QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
+template <bool SH>
+QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
                    float ox, float oy, float oz, float rx, float ry, float rz,
                    float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
                    float t_min, float t_buf, float t,
@@ -227,7 +258,7 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
     const float hy = qr_add(qr_mul(ry, t), oy);
     const float hz = qr_add(qr_mul(rz, t), oz);
 
-    if (QR_D_TRM(d) != 0)
+    if (d & QR_D_TRM_MASK)
     {
         lx = qr_add(qr_mul(lr0, t), ld0);
         ly = qr_add(qr_mul(lr1, t), ld1);
@@ -241,12 +272,12 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
     }
 
     /* conic singularity solver 1706-1856 (lane semantics: hmask decides) */
-    const uint32_t conic = QR_D_CONIC(d);
-    if (conic != 0 && dmask)
+    if ((d & QR_D_CONIC_MASK) && dmask)
     {
+        const uint32_t conic = QR_D_CONIC(d);
         const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
-        const qr_f4 q1 = q[1];
-        const float t_eps = q[7].z;
+        const qr_f4 q1 = QR_SURF(v, si, 1);
+        const float t_eps = QR_SURF(v, si, 7).z;
         const float li = qr_pick3(iI, lx, ly, lz), lj = qr_pick3(iJ, lx, ly, lz), lk = qr_pick3(iK, lx, ly, lz);
         float a0 = qr_mul(li, li);
         if (conic != 2)
@@ -292,20 +323,19 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
     }
 
     /* axis min/max 1874-1927 */
-    const uint32_t mm = QR_D_MM(d);
     bool m = true;
-    if (mm != 0)
+    if (d & QR_D_MM_MASK)
     {
-        const qr_f4 q3 = q[3], q4 = q[4];
-        if (mm & 1)  m = m && (q3.x <= lx);
-        if (mm & 8)  m = m && qr_ge(q4.x, lx);
-        if (mm & 2)  m = m && (q3.y <= ly);
-        if (mm & 16) m = m && qr_ge(q4.y, ly);
-        if (mm & 4)  m = m && (q3.z <= lz);
-        if (mm & 32) m = m && qr_ge(q4.z, lz);
+        const qr_f4 q3 = QR_SURF(v, si, 3), q4 = QR_SURF(v, si, 4);
+        if (d & (1u << 21)) m = m && (q3.x <= lx);
+        if (d & (8u << 21)) m = m && qr_ge(q4.x, lx);
+        if (d & (2u << 21)) m = m && (q3.y <= ly);
+        if (d & (16u << 21)) m = m && qr_ge(q4.y, ly);
+        if (d & (4u << 21)) m = m && (q3.z <= lz);
+        if (d & (32u << 21)) m = m && qr_ge(q4.z, lz);
     }
 
-    if (!QR_D_HASCLIP(d))
+    if (!(d & QR_D_HASCLIP_MASK))
     {
         return m;
     }
@@ -314,27 +344,27 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
      * the packet; a lone sample may stop as soon as its mask is clear and no
      * accumulator is open (a cleared mask can only come back through an
      * accum enter/leave pair). */
-    const int s_trnode = (int)qr_f2u(q[4].w);
-    const uint32_t c_def = qr_f2u(q[7].w);
+    const int s_trnode = (int)qr_f2u(QR_SURF(v, si, 4).w);
+    const uint32_t c_def = qr_f2u(QR_SURF(v, si, 7).w);
     float nx = 0.0f, ny = 0.0f, nz = 0.0f;      /* NRM_X/Y/Z */
     float ni = 0.0f, nj = 0.0f, nk = 0.0f;      /* NRM_I/J/K */
     bool  acc = false, in_acc = false;
     int   redx = QR_NIL;
     bool  last = true;
 
-    for (int di = (int)qr_f2u(q[3].w); di != QR_NIL; )
+    for (int di = (int)qr_f2u(QR_SURF(v, si, 3).w); di != QR_NIL; )
     {
         if (!m && !in_acc)
         {
             return false;
         }
-        const qr_elem ce = v.elems[di];
+        const qr_kelem ce = v.elems[di];
         const int cur = di;
         di = ce.next;
 
         if (ce.simd == QR_NIL)
         {
-            if (ce.data_i > 0)
+            if (ce.op > 0)
             {
                 m = !m && acc;                  /* annpx: ~mask & C_ACC */
                 in_acc = false;
@@ -348,12 +378,12 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
             continue;
         }
 
-        const qr_f4 *cq = v.surf + (size_t)ce.simd * QR_KSURF_QUADS;
-        const qr_f4 c0 = cq[0];
+        const int ci = ce.simd;
+        const qr_f4 c0 = QR_SURF(v, ci, 0);
         const uint32_t cd = qr_f2u(c0.w);
         bool have_local = false;
 
-        if (!QR_D_ARRAY(cd))
+        if (!(cd & QR_D_ARRAY_MASK))
         {
             if (redx != QR_NIL)
             {
@@ -365,12 +395,12 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
             }
         }
         else
-        if (ce.simd == s_trnode)
+        if (ci == s_trnode)
         {
             nx = qr_add(lx, q0.x);
             ny = qr_add(ly, q0.y);
             nz = qr_add(lz, q0.z);
-            redx = ce.data_p;
+            redx = ce.aux;
             continue;
         }
 
@@ -379,14 +409,15 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
             nx = qr_sub(hx, c0.x);
             ny = qr_sub(hy, c0.y);
             nz = qr_sub(hz, c0.z);
-            if (QR_D_TRM(cd) != 0)
+            if (cd & QR_D_TRM_MASK)
             {
                 float o4, o5, o6;
-                qr_xform(cq, QR_D_TRM(cd), nx, ny, nz, o4, o5, o6);
-                if (QR_D_ARRAY(cd))
+                qr_xform(QR_SURF(v, ci, 5), QR_SURF(v, ci, 6), QR_SURF(v, ci, 7).x, QR_D_TRM(cd),
+                         nx, ny, nz, o4, o5, o6);
+                if (cd & QR_D_ARRAY_MASK)
                 {
                     nx = o4; ny = o5; nz = o6;
-                    redx = ce.data_p;
+                    redx = ce.aux;
                     continue;
                 }
                 ni = o4; nj = o5; nk = o6;
@@ -394,7 +425,7 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
         }
 
         /* clipper evaluators: PL_clp 4198-4208, QD_clp 4910-4951, TP_clp 4341-4370 */
-        const bool csh = QR_D_SHIFT(cd) != 0;
+        const bool csh = (cd & QR_D_SHIFT_MASK) != 0;
         const float p0 = csh ? ni : nx, p1 = csh ? nj : ny, p2 = csh ? nk : nz;
         const uint32_t ctag = QR_D_CLIP(cd);
         if (ctag != 0)
@@ -406,13 +437,13 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
             }
             else
             {
-                const qr_f4 c1 = cq[1];
+                const qr_f4 c1 = QR_SURF(v, ci, 1);
                 float a4 = qr_mul(qr_mul(p0, p0), c1.x);
                 float a5 = qr_mul(qr_mul(p1, p1), c1.y);
                 float a6 = qr_mul(qr_mul(p2, p2), c1.z);
                 if (ctag == 2)
                 {
-                    const qr_f4 c2 = cq[2];
+                    const qr_f4 c2 = QR_SURF(v, ci, 2);
                     a4 = qr_sub(a4, qr_mul(qr_add(c2.x, c2.x), p0));
                     a5 = qr_sub(a5, qr_mul(qr_add(c2.y, c2.y), p1));
                     a6 = qr_sub(a6, qr_mul(qr_add(c2.z, c2.z), p2));
@@ -422,7 +453,7 @@ QR_HD bool qr_clip(const qr_view &v, const qr_f4 *q, uint32_t d, const qr_f4 q0,
                 val = qr_add(a4, a6);
             }
             /* APPLY_CLIP 488-496 */
-            last = ce.data_i < 0 ? qr_ge(val, 0.0f) : (val <= 0.0f);
+            last = ce.op < 0 ? qr_ge(val, 0.0f) : (val <= 0.0f);
         }
         m = m && last;
     }
@@ -451,18 +482,22 @@ QR_HD uint32_t qr_side_props(uint32_t packed, int side)
  *   mode SHADOW : returns true when the sample is in shadow (first occluder)
  * (plx, ply, plz) is the stored local hit of the originating level (NRM_I/J/K
  * of the previous context), used when the ray starts on the surface tested.
+ *
+ * Transform caching (tracer.cpp:1377-1421, 1483-1500): while a transform node
+ * (array with a matrix) is open, (tdx,tdy,tdz) is the ray origin and
+ * (cr0,cr1,cr2) the ray direction in the node's space; outside, (cr0..) is the
+ * world ray.  Which elements run inside a node is compiled into e.op.
  */
-QR_HD bool qr_walk(const qr_view &v, int head, int mode,
+template <bool SH>
+QR_HD bool qr_walk(const qr_view<SH> &v, int head, int mode,
                    float ox, float oy, float oz, float rx, float ry, float rz,
                    float t_min, float t_max, int p_obj, int p_flg,
                    float plx, float ply, float plz,
                    float &t_buf, int &best_si, int &best_side,
                    float &blx, float &bly, float &blz)
 {
-    qr_walk_state w;
-    w.dx = w.dy = w.dz = w.di = w.dj = w.dk = 0.0f;
-    w.ri = w.rj = w.rk = 0.0f;
-    w.l_obj = QR_NIL;
+    float tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;   /* DFF_X/Y/Z of the open trnode */
+    float cr0 = rx, cr1 = ry, cr2 = rz;         /* RAY_X/Y/Z, or RAY_I/J/K of the open trnode */
 
     t_buf = t_max;
     best_si = QR_NIL;
@@ -471,75 +506,73 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
     int ei = head;
     while (ei != QR_NIL)
     {
-        const qr_elem e = v.elems[ei];
-        const int cur = ei;
+        const qr_kelem e = v.elems[ei];
         ei = e.next;
 
         const int si = e.simd;
-        const qr_f4 *q = v.surf + (size_t)si * QR_KSURF_QUADS;
-        const qr_f4 q0 = q[0];
+        const uint32_t op = (uint32_t)e.op;
+        const qr_f4 q0 = QR_SURF(v, si, 0);
         const uint32_t d = qr_f2u(q0.w);
         const bool same = (si == p_obj);
-        const bool shift = QR_D_SHIFT(d) != 0;
-        const uint32_t trm = QR_D_TRM(d);
 
-        /* 1352-1373: reuse the stored local hit of the previous context */
-        if (same)
+        /* ---- object prologue, OO_ini .. OO_trm 1348-1558 ---- */
+        if (op & QR_OP_OPEN)
         {
-            if (shift) { w.di = plx; w.dj = ply; w.dk = plz; }
-            else       { w.dx = plx; w.dy = ply; w.dz = plz; }
+            /* array with a matrix: transform origin diff and ray once for the
+             * elements up to the node's last one (1483-1496) */
+            const qr_f4 q5 = QR_SURF(v, si, 5), q6 = QR_SURF(v, si, 6);
+            const float tckz = QR_SURF(v, si, 7).x;
+            qr_xform(q5, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                     tdx, tdy, tdz);
+            qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
+            continue;                           /* srf_t[0] == 0: nothing to intersect */
         }
 
-        if (!QR_D_ARRAY(d) && w.l_obj != QR_NIL)
+        float ld0, ld1, ld2;                    /* DFF in the surface's field set */
+        float lr0 = cr0, lr1 = cr1, lr2 = cr2;  /* RAY in the surface's field set */
+
+        if (same)
         {
-            /* 1385-1417: transform caching under a trnode */
-            if (!same)
+            /* 1352-1373: secondary ray leaving this very surface reuses the
+             * stored local hit as its local diff */
+            ld0 = plx; ld1 = ply; ld2 = plz;
+            if (op & QR_OP_OWNTRM)
             {
-                w.di = qr_sub(w.dx, q0.x);
-                w.dj = qr_sub(w.dy, q0.y);
-                w.dk = qr_sub(w.dz, q0.z);
+                qr_xform(QR_SURF(v, si, 5), QR_SURF(v, si, 6), QR_SURF(v, si, 7).x, QR_D_TRM(d),
+                         rx, ry, rz, lr0, lr1, lr2);
             }
-            if (cur == w.l_obj) w.l_obj = QR_NIL;
+        }
+        else
+        if (op & QR_OP_CACHED)
+        {
+            /* 1385-1406: child of the open trnode */
+            ld0 = qr_sub(tdx, q0.x);
+            ld1 = qr_sub(tdy, q0.y);
+            ld2 = qr_sub(tdz, q0.z);
         }
         else
         {
-            /* OO_dff 1419-1556 */
-            bool do_ray = same;
-            if (!same)
+            /* OO_dff 1429-1556 */
+            ld0 = qr_sub(ox, q0.x);
+            ld1 = qr_sub(oy, q0.y);
+            ld2 = qr_sub(oz, q0.z);
+            if (op & QR_OP_OWNTRM)
             {
-                w.dx = qr_sub(ox, q0.x);
-                w.dy = qr_sub(oy, q0.y);
-                w.dz = qr_sub(oz, q0.z);
-                if (trm != 0)
-                {
-                    float o4, o5, o6;
-                    qr_xform(q, trm, w.dx, w.dy, w.dz, o4, o5, o6);
-                    if (QR_D_ARRAY(d))
-                    {
-                        w.dx = o4; w.dy = o5; w.dz = o6;
-                        w.l_obj = e.data_p;
-                    }
-                    else
-                    {
-                        w.di = o4; w.dj = o5; w.dk = o6;
-                    }
-                    do_ray = true;
-                }
-            }
-            if (do_ray)
-            {
-                qr_xform(q, trm, rx, ry, rz, w.ri, w.rj, w.rk);
+                const qr_f4 q5 = QR_SURF(v, si, 5), q6 = QR_SURF(v, si, 6);
+                const float tckz = QR_SURF(v, si, 7).x;
+                qr_xform(q5, q6, tckz, QR_D_TRM(d), ld0, ld1, ld2, ld0, ld1, ld2);
+                qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, lr0, lr1, lr2);
             }
         }
-
-        /* ray / diff in the surface's field set (a_sgn[L] shift) */
-        const float lr0 = shift ? w.ri : rx, lr1 = shift ? w.rj : ry, lr2 = shift ? w.rk : rz;
-        const float ld0 = shift ? w.di : w.dx, ld1 = shift ? w.dj : w.dy, ld2 = shift ? w.dk : w.dz;
+        if (op & QR_OP_CLOSE)
+        {
+            cr0 = rx; cr1 = ry; cr2 = rz;       /* last element of the open trnode */
+        }
 
         /* AR_ptr 3955-4054: bounding volume of an array */
-        if (e.data_i == 1)
+        if (op & QR_OP_BV)
         {
-            const qr_f4 q1 = q[1];
+            const qr_f4 q1 = QR_SURF(v, si, 1);
             float x1 = lr0;
             float x0 = qr_mul(q1.x, x1);
             float x5 = ld0;
@@ -569,10 +602,12 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
             x3 = qr_sub(x3, x5);
             if (!(0.0f <= x3))
             {
-                /* AR_skp: jump behind the array's last leaf */
-                const int lastleaf = e.data_p;
-                if (lastleaf == w.l_obj) w.l_obj = QR_NIL;
-                ei = v.elems[lastleaf].next;
+                /* AR_skp: continue behind the array's last leaf */
+                ei = e.aux;
+                if (op & QR_OP_SKIPCLOSE)
+                {
+                    cr0 = rx; cr1 = ry; cr2 = rz;
+                }
             }
             continue;
         }
@@ -591,12 +626,12 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
             const float rk = qr_sgn(qr_pick3(k, lr0, lr1, lr2), sg);
             if (!(0.0f != rk)) continue;
             const float t = qr_div(dk, rk);
-            if (!qr_clip(v, q, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
-                         t_min, t_buf, t, false, 0u, 0, lx, ly, lz)) continue;
+            if (!qr_clip<SH>(v, si, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
+                             t_min, t_buf, t, false, 0u, 0, lx, ly, lz)) continue;
             const int side = (rk < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
             if (mode == QR_MODE_SHADOW)
             {
-                if (qr_casts_shadow(qr_side_props(qr_f2u(q[2].w), side))) return true;
+                if (qr_casts_shadow(qr_side_props(qr_f2u(QR_SURF(v, si, 2).w), side))) return true;
                 continue;
             }
             t_buf = t; best_si = si; best_side = side;
@@ -605,7 +640,8 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
         }
 
         float a_val, b_val, c_val, d_val;
-        const qr_f4 q1 = q[1];
+        const qr_f4 q1 = QR_SURF(v, si, 1);
+        const qr_f4 q2 = QR_SURF(v, si, 2);
 
         if (tag == 3)
         {
@@ -626,7 +662,6 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
         else
         {
             /* QD_ptr 4378-4447 */
-            const qr_f4 q2 = q[2];
             float a7 = qr_sub(qr_mul(q1.x, ld0), q2.x);
             float a3 = qr_mul(lr0, a7);
             float a1 = qr_mul(lr0, qr_mul(q1.x, lr0));
@@ -658,8 +693,9 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
 
         /* QD_rts 4449-4547 */
         if (!(0.0f <= d_val)) continue;
+        const qr_f4 q7 = QR_SURF(v, si, 7);
         const float b = qr_neg(b_val);
-        const bool dmask = d_val < q[7].y;
+        const bool dmask = d_val < q7.y;
         const float sd = qr_u2f(qr_f2u(qr_sqrt(d_val)) ^ (qr_f2u(b) & 0x80000000u));
         const float bd = qr_add(b, sd);
         const bool m_pos = 0.0f <= sd;
@@ -683,7 +719,7 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
             float a2 = qr_u2f(qr_f2u(qr_sub(t1, t2)) ^ amask);
             const bool fm = 0.0f <= a2;
             a2 = fm ? a2 : 0.0f;
-            const float a5 = qr_abs(qr_mul(fm ? q[7].z : 0.0f, t1));
+            const float a5 = qr_abs(qr_mul(fm ? q7.z : 0.0f, t1));
             a2 = qr_sub(qr_mul(a2, -0.5f), a5);
             uint32_t u2 = qr_f2u(a2) ^ amask;
             if (!(k1 && k2)) u2 = 0;
@@ -715,11 +751,11 @@ QR_HD bool qr_walk(const qr_view &v, int head, int mode,
                 k = dd != 0.0f;
             }
             if (!k) continue;
-            if (!qr_clip(v, q, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
-                         t_min, t_buf, t, dmask, amask, side, lx, ly, lz)) continue;
+            if (!qr_clip<SH>(v, si, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
+                             t_min, t_buf, t, dmask, amask, side, lx, ly, lz)) continue;
             if (mode == QR_MODE_SHADOW)
             {
-                if (qr_casts_shadow(qr_side_props(qr_f2u(q[2].w), side))) return true;
+                if (qr_casts_shadow(qr_side_props(qr_f2u(q2.w), side))) return true;
                 break;
             }
             t_buf = t; best_si = si; best_side = side;
@@ -812,7 +848,8 @@ QR_HD float qr_fresnel(float c, float rfr, float x0, float x7)
  * Trace one primary sample.  "stack" needs QR_STACK_DEPTH frames.
  * Returns the sample colour (before clamp / AA / gamma) and the primary T_BUF.
  */
-QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
+template <bool SH>
+QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                            qr_frame *stack, float &out_r, float &out_g, float &out_b,
                            float &out_t, qr_counters &cnt)
 {
@@ -866,7 +903,7 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
         {
             plx = stack[lvl - 1].loc[0]; ply = stack[lvl - 1].loc[1]; plz = stack[lvl - 1].loc[2];
         }
-        const bool res = qr_walk(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
+        const bool res = qr_walk<SH>(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
                                  p_obj, p_flg, plx, ply, plz,
                                  t_buf, best_si, best_side, blx, bly, blz);
         bool lights_phase = false;
@@ -875,14 +912,13 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
         if (mode == QR_MODE_SHADOW)
         {
             /* LT_ret 2833-3151: light contribution unless occluded */
-            const qr_elem le = v.elems[li];
+            const qr_kelem le = v.elems[li];
             if (!res)
             {
-                const qr_f4 *lq = v.lgt + (size_t)le.simd * QR_KLGT_QUADS;
-                const qr_f4 l1 = lq[1], l2 = lq[2];
-                const qr_f4 sh0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
+                const qr_f4 l1 = QR_LGT(v, le.simd, 1), l2 = QR_LGT(v, le.simd, 2);
+                const qr_f4 sh0 = QR_SHADE(v, cur_si, 0);
                 const int mi = (int)qr_f2u((l_flg & 1) ? sh0.y : sh0.x);
-                const qr_f4 m2 = v.mat[(size_t)mi * QR_KMAT_QUADS + 2];
+                const qr_f4 m2 = QR_MAT(v, mi, 2);
                 const uint32_t props = (uint32_t)l_flg;
 
                 /* (rx, ry, rz) holds NEW_X/Y/Z = light vector */
@@ -974,15 +1010,13 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
             {
                 /* ---------------- SHADE ---------------- */
                 cur_si = best_si;
-                const qr_f4 *q = v.surf + (size_t)cur_si * QR_KSURF_QUADS;
-                const qr_f4 q1 = q[1], q2 = q[2];
-                const uint32_t d = qr_f2u(q[0].w);
+                const qr_f4 q1 = QR_SURF(v, cur_si, 1), q2 = QR_SURF(v, cur_si, 2);
+                const uint32_t d = qr_f2u(QR_SURF(v, cur_si, 0).w);
                 const int side = best_side;
                 const uint32_t props = (uint32_t)side | qr_side_props(qr_f2u(q2.w), side);   /* FETCH_PROP */
                 l_flg = (int)props;
-                const qr_f4 s0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
+                const qr_f4 s0 = QR_SHADE(v, cur_si, 0);
                 const int mi = (int)qr_f2u(side ? s0.y : s0.x);
-                const qr_f4 *mq = v.mat + (size_t)mi * QR_KMAT_QUADS;
 
                 lrx = rx; lry = ry; lrz = rz;
                 hx = qr_add(qr_mul(rx, t_buf), ox);
@@ -1034,13 +1068,13 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
 
                 if (props & QR_PROP_NORMAL)
                 {
-                    if (QR_D_TRM(d) != 0)
+                    if (d & QR_D_TRM_MASK)
                     {
                         /* MT_nrm 2184-2259: transposed matrix of the trnode */
-                        const qr_f4 *t = v.surf + (size_t)(int)qr_f2u(q[4].w) * QR_KSURF_QUADS;
-                        const qr_f4 t5 = t[5], t6 = t[6];
-                        const float tck_z = t[7].x;
-                        const uint32_t ttrm = QR_D_TRM(qr_f2u(t[0].w));
+                        const int ti = (int)qr_f2u(QR_SURF(v, cur_si, 4).w);
+                        const qr_f4 t5 = QR_SURF(v, ti, 5), t6 = QR_SURF(v, ti, 6);
+                        const float tck_z = QR_SURF(v, ti, 7).x;
+                        const uint32_t ttrm = QR_D_TRM(qr_f2u(QR_SURF(v, ti, 0).w));
                         float x4 = qr_mul(t5.x, n0);
                         float x5 = qr_mul(t6.x, n1);
                         float x6 = qr_mul(tck_z, n2);
@@ -1072,11 +1106,11 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                 }
 
                 /* MT_mat 2286-2327: texel */
-                const qr_f4 m1 = mq[1], m4 = mq[4];
+                const qr_f4 m1 = QR_MAT(v, mi, 1), m4 = QR_MAT(v, mi, 4);
                 uint32_t p = 0;
                 if (props & QR_PROP_TEXTURE)
                 {
-                    const qr_f4 m0 = mq[0];
+                    const qr_f4 m0 = QR_MAT(v, mi, 0);
                     const uint32_t ys = qr_f2u(m1.z);
                     float tx = (ys & 0x100u) ? tex_v : tex_u;
                     float ty = (ys & 0x200u) ? tex_v : tex_u;
@@ -1117,8 +1151,8 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
             bool go_shadow = false;
             while (li != QR_NIL)
             {
-                const qr_elem le = v.elems[li];
-                const qr_f4 l0 = v.lgt[(size_t)le.simd * QR_KLGT_QUADS];
+                const qr_kelem le = v.elems[li];
+                const qr_f4 l0 = QR_LGT(v, le.simd, 0);
                 const float x1 = qr_sub(l0.x, hx);
                 const float x2 = qr_sub(l0.y, hy);
                 const float x3 = qr_sub(l0.z, hz);
@@ -1132,7 +1166,7 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                     rx = x1; ry = x2; rz = x3;
                     t_min = 0.0f;
                     t_max = l0.w;
-                    head = le.data_p;
+                    head = le.aux;
                     mode = QR_MODE_SHADOW;
                     p_obj = cur_si;
                     p_flg = l_flg | QR_FLAG_PASS_BACK | QR_FLAG_SHAD;
@@ -1180,12 +1214,11 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
 
             const int side = l_flg & 1;
             const uint32_t props = (uint32_t)l_flg;
-            const qr_f4 s0 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS];
-            const qr_f4 s1 = v.shade[(size_t)cur_si * QR_KSHADE_QUADS + 1];
+            const qr_f4 s0 = QR_SHADE(v, cur_si, 0);
+            const qr_f4 s1 = QR_SHADE(v, cur_si, 1);
             const int mi = (int)qr_f2u(side ? s0.y : s0.x);
-            const qr_f4 *mq = v.mat + (size_t)mi * QR_KMAT_QUADS;
-            const qr_f4 m3 = mq[3];
-            const float m_c_rfl = mq[2].w;
+            const qr_f4 m3 = QR_MAT(v, mi, 3);
+            const float m_c_rfl = QR_MAT(v, mi, 2).w;
             const float m_c_trn = m3.x, m_c_rfr = m3.y, m_rfr_2 = m3.z, m_c_rcp = m3.w;
 
             bool push = false;
@@ -1296,7 +1329,7 @@ QR_HD void qr_trace_sample(const qr_view &v, int px, int py, int lane4,
                         a4 = qr_add(a4, a4);
                         a0 = qr_mul(a0, a0);
                         a6 = qr_mul(a6, a6);
-                        a6 = qr_add(a6, mq[4].x);
+                        a6 = qr_add(a6, QR_MAT(v, mi, 4).x);
                         float a1 = qr_mul(a0, a6);
                         a0 = qr_add(a0, a6);
                         a1 = qr_add(a1, 1.0f);

@@ -24,6 +24,8 @@
 
 #include <stdint.h>
 #include <string.h>
+#include <utility>
+#include <vector>
 #include "qr_scene_blob.h"
 
 #define QR_KSCENE_FLAG   0x4B534331u    /* "1CSK" */
@@ -38,6 +40,32 @@ struct __align__(16) qr_f4 { float x, y, z, w; };
 #else
 struct alignas(16) qr_f4 { float x, y, z, w; };
 #endif
+
+/*
+ * List element of the image ("compiled" rt_ELEM).  The reference tracks, while
+ * it walks a surface list, whether a transform node is open (ctx_LOCAL(OBJ),
+ * tracer.cpp:1377-1421, 1492-1496, 4047-4053); that state only depends on the
+ * list, not on the ray, so it is resolved here, once per upload:
+ *   surface lists  simd = surface, aux = element to continue at when the
+ *                  bounding volume is missed (next of the array's last leaf),
+ *                  op  = QR_OP_BV | QR_OP_CACHED
+ *   light lists    simd = light, aux = head of the light's shadow list
+ *   clip lists     simd = clipper surface or QR_NIL (accum marker),
+ *                  aux = trnode's last element (array clippers), op = clip
+ *                  side / accum marker (rt_ELEM.data, +-1)
+ */
+#if defined(__CUDACC__)
+struct __align__(16) qr_kelem { int32_t simd, next, aux, op; };
+#else
+struct alignas(16) qr_kelem { int32_t simd, next, aux, op; };
+#endif
+
+#define QR_OP_BV        1   /* bounding-volume element of an array (elm.data & 3 == 1) */
+#define QR_OP_CACHED    2   /* child of the open transform node: diff = node diff - pos */
+#define QR_OP_OPEN      4   /* array with a matrix: opens a transform node */
+#define QR_OP_OWNTRM    8   /* surface with its own matrix, outside any open node */
+#define QR_OP_CLOSE    16   /* last element of the open transform node */
+#define QR_OP_SKIPCLOSE 32  /* a missed bounding volume skips past the node's last element */
 
 /*
  * ksurf quads (traversal):
@@ -81,6 +109,12 @@ struct alignas(16) qr_f4 { float x, y, z, w; };
 #define QR_D_MAP(d, i)  (((d) >> (15 + 2 * (i))) & 3u)
 #define QR_D_MM(d)      (((d) >> 21) & 63u)
 #define QR_D_HASCLIP(d) (((d) >> 27) & 1u)
+#define QR_D_CONIC_MASK   (3u << 6)
+#define QR_D_TRM_MASK     (3u << 8)
+#define QR_D_SHIFT_MASK   (1u << 10)
+#define QR_D_ARRAY_MASK   (1u << 11)
+#define QR_D_MM_MASK      (63u << 21)
+#define QR_D_HASCLIP_MASK (1u << 27)
 
 /* host-side packer (plain inline functions; never called from device code) */
 
@@ -103,8 +137,12 @@ static inline size_t qr_kscene_size(const void *blob)
     return off;
 }
 
-/* build the kscene image of "blob" in "out" (qr_kscene_size bytes, 16-aligned) */
-static inline void qr_kscene_pack(const void *blob, void *out)
+/*
+ * Build the kscene image of "blob" in "out" (qr_kscene_size bytes, 16-aligned).
+ * Returns 0, or -1 when a surface list is not well nested (an element would be
+ * reached both inside and outside an open transform node).
+ */
+static inline int qr_kscene_pack(const void *blob, void *out)
 {
     const uint8_t *b = (const uint8_t *)blob;
     uint8_t *o = (uint8_t *)out;
@@ -112,6 +150,8 @@ static inline void qr_kscene_pack(const void *blob, void *out)
     const qr_surface  *sf = (const qr_surface  *)(b + h->off_surf);
     const qr_material *mt = (const qr_material *)(b + h->off_mat);
     const qr_light    *lg = (const qr_light    *)(b + h->off_lgt);
+    const qr_elem     *el = (const qr_elem     *)(b + h->off_elem);
+    const int32_t     *tl = (const int32_t     *)(b + h->off_tiles);
 
     qr_blob_header k = *h;
     uint32_t off = sizeof(qr_blob_header);
@@ -190,9 +230,104 @@ static inline void qr_kscene_pack(const void *blob, void *out)
         q[2].x = l.a_lnr;  q[2].y = l.a_cnt;  q[2].z = 0.0f;     q[2].w = 0.0f;
     }
 
-    memcpy(o + k.off_elem,   b + h->off_elem,   (size_t)h->n_elem * sizeof(qr_elem));
+    /* ---- compile the lists ---- */
+    qr_kelem *ke = (qr_kelem *)(o + k.off_elem);
+    const int ne = h->n_elem;
+    for (int i = 0; i < ne; i++)
+    {
+        ke[i].simd = el[i].simd;
+        ke[i].next = el[i].next;
+        ke[i].aux  = el[i].data_p;
+        ke[i].op   = el[i].data_i;      /* light / clip lists keep the raw data */
+    }
+    {
+        /* state[i]: the open trnode's last element when element i of a surface
+         * list is processed (QR_NIL none), -2 = not reached yet */
+        std::vector<int32_t> state((size_t)ne, -2);
+        std::vector<int32_t> roots;
+        for (int t = 0; t < h->n_tiles; t++) roots.push_back(tl[t]);
+        for (int i = 0; i < h->n_surf; i++)
+        {
+            roots.push_back(sf[i].lst_srf[0]);
+            roots.push_back(sf[i].lst_srf[1]);
+            for (int sd = 0; sd < 2; sd++)
+            {
+                int guard = 0;
+                for (int li = sf[i].lst_lgt[sd]; li != QR_NIL && guard <= ne; li = el[li].next, guard++)
+                {
+                    roots.push_back(el[li].data_p);
+                }
+            }
+        }
+        /* (element, state) pairs still to expand */
+        std::vector<std::pair<int32_t, int32_t> > work;
+        for (size_t r = 0; r < roots.size(); r++)
+        {
+            if (roots[r] != QR_NIL) work.push_back(std::make_pair(roots[r], (int32_t)QR_NIL));
+        }
+        while (!work.empty())
+        {
+            int32_t i = work.back().first, lobj = work.back().second;
+            work.pop_back();
+            while (i != QR_NIL)
+            {
+                if (i < 0 || i >= ne) return -1;
+                if (state[i] != -2)
+                {
+                    if (state[i] != lobj) return -1;
+                    break;                              /* suffix already compiled */
+                }
+                state[i] = lobj;
+                const qr_elem &e = el[i];
+                if (e.simd < 0 || e.simd >= h->n_surf) return -1;
+                const qr_surface &s = sf[e.simd];
+                const bool is_array = s.srf_t[3] < 0;
+                int32_t op = 0;
+                if (!is_array && lobj != QR_NIL)
+                {
+                    if (s.a_sgn[3] == 0) return -1;     /* child without the field shift */
+                    op |= QR_OP_CACHED;
+                    if (i == lobj)
+                    {
+                        op |= QR_OP_CLOSE;
+                        lobj = QR_NIL;
+                    }
+                }
+                else
+                if (is_array && s.a_map[3] != 0)
+                {
+                    op |= QR_OP_OPEN;
+                    lobj = e.data_p;                    /* tracer.cpp:1492-1496 */
+                }
+                else
+                if (is_array && lobj != QR_NIL)
+                {
+                    return -1;                          /* plain array inside an open node */
+                }
+                else
+                if (!is_array && s.a_map[3] != 0)
+                {
+                    op |= QR_OP_OWNTRM;
+                }
+                int32_t aux = QR_NIL;
+                if (e.data_i == 1)
+                {
+                    op |= QR_OP_BV;
+                    if (e.data_p == lobj) op |= QR_OP_SKIPCLOSE;
+                    if (e.data_p < 0 || e.data_p >= ne) return -1;
+                    aux = el[e.data_p].next;            /* tracer.cpp:4042-4054 */
+                    const int32_t after = e.data_p == lobj ? (int32_t)QR_NIL : lobj;
+                    if (aux != QR_NIL) work.push_back(std::make_pair(aux, after));
+                }
+                ke[i].op = op;
+                ke[i].aux = aux;
+                i = e.next;
+            }
+        }
+    }
     memcpy(o + k.off_tiles,  b + h->off_tiles,  (size_t)h->n_tiles * sizeof(int32_t));
     memcpy(o + k.off_texels, b + h->off_texels, (size_t)h->n_texels * sizeof(uint32_t));
+    return 0;
 }
 
 #endif /* QR_KSCENE_H */

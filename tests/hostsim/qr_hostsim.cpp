@@ -31,9 +31,9 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     const size_t kbytes = qr_kscene_size(blob);
     void *kimg = aligned_alloc(64, (kbytes + 63) & ~(size_t)63);
     if (kimg == NULL) return -3;
-    qr_kscene_pack(blob, kimg);
-    qr_view v;
-    qr_view_init(v, kimg, kimg);
+    if (qr_kscene_pack(blob, kimg) != 0) { free(kimg); return -4; }
+    qr_view<false> v;
+    qr_view_init(v, kimg);
 
     const int fsaa = h->fsaa, spp = 1 << fsaa;
     static const int lane_px[3][4] = { {0, 1, 2, 3}, {0, 0, 1, 1}, {0, 0, 0, 0} };
@@ -54,7 +54,7 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
             {
                 const int px = x + lane_px[fsaa][l];
                 float col[3];
-                qr_trace_sample(v, px, y, l, stack, col[0], col[1], col[2], tb[l], cnt);
+                qr_trace_sample<false>(v, px, y, l, stack, col[0], col[1], col[2], tb[l], cnt);
                 primary++;
                 for (int k = 0; k < 3; k++) c[k][l] = qr_clamp1(col[k]);
             }
