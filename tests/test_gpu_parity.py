@@ -159,3 +159,23 @@ def test_gpu_full_size_properties(entry, ctx):
     assert np.array_equal(band[512:640], full[512:640])
     assert not band[:512].any() and not band[640:].any()
     assert np.array_equal(ctx.render_frame(), full)
+
+
+def test_gpu_multi_device_context(entry, pkg):
+    """One context over several GPUs: tile-row bands per GPU, peer gather to
+    GPU 0.  Needs >= 2 visible devices."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    blob, ref, _ = entry.load_golden("demo03_a4g")
+    for ndev in sorted({2, min(n, 4), n}):
+        c = pkg.Context(list(range(ndev)))
+        try:
+            c.upload(blob)
+            got = c.render_frame()
+            assert int((got != ref).sum()) == 0, ndev
+            counts = c.ray_counts()
+            assert counts["primary"] == ref.size << 2
+        finally:
+            c.close()
