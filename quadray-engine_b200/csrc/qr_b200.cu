@@ -175,6 +175,8 @@ qr_render_kernel(const qr_launch p)
                     : smp;
 
     qr_frame stack[QR_STACK_DEPTH + 1];
+    /* per-thread best-hit slot behind the staged scene (16 B per thread) */
+    const qr_slot best = smem_u32(qr_smem) + p.stage_bytes + threadIdx.x * 16u;
     qr_counters cnt;
     cnt.shadow = cnt.reflect = cnt.refract = 0;
     unsigned int n_primary = 0;
@@ -204,7 +206,7 @@ qr_render_kernel(const qr_launch p)
             const bool live = px < x_res;
             if (live)
             {
-                qr_trace_sample<STAGED>(v, px, y, lane4, stack, col[0], col[1], col[2], t, cnt);
+                qr_trace_sample<STAGED>(v, px, y, lane4, stack, best, col[0], col[1], col[2], t, cnt);
                 n_primary++;
                 if (p.t_out != NULL)
                 {
@@ -349,6 +351,7 @@ struct qr_ctx
     uint64_t        rays[4];
     int             shape;          /* index into g_shapes */
     cudaFuncAttributes fattr;
+    qr_kpacker      packer;
     char            err[512];
 };
 
@@ -402,7 +405,6 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
     {
         return qr_fail(NULL, QR_E_ARG, "qr_init: out of memory");
     }
-    memset(ctx, 0, sizeof(*ctx));
 
     int cur = 0;
     cudaGetDevice(&cur);
@@ -586,11 +588,16 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         return rc;
     }
     const qr_blob_header *h = (const qr_blob_header *)blob;
-    const size_t n = qr_kscene_size(blob);
 
-    /* pinned staging: the caller's buffer is free again when we return.  The
-     * blob is not copied verbatim: it is compiled into the packed kscene
-     * image (qr_kscene.h) on the way into the staging buffer. */
+    /* the blob is not copied verbatim: it is compiled into the packed kscene
+     * image (qr_kscene.h) on the way into the pinned staging buffer */
+    qr_kpacker &pk = ctx->packer;
+    if (pk.plan(blob) != 0)
+    {
+        return qr_fail(ctx, QR_E_BLOB, "scene blob: malformed or not well nested list");
+    }
+    const size_t n = pk.bytes();
+
     qr_dev &d0 = ctx->dev[0];
     QR_CUDA(ctx, cudaSetDevice(d0.id));
     /* the previous frame's H2D copies read the staging buffer */
@@ -603,10 +610,7 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     {
         return rc;
     }
-    if (qr_kscene_pack(blob, d0.blob_h) != 0)
-    {
-        return qr_fail(ctx, QR_E_BLOB, "scene blob: surface list is not well nested");
-    }
+    pk.write(d0.blob_h);
     const qr_blob_header *kh = (const qr_blob_header *)d0.blob_h;
 
     for (int i = 0; i < ctx->ndev; i++)
@@ -626,7 +630,8 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
 
     /* shared-memory staging of the kscene prefix */
     const uint32_t prefix = kh->off_elem;
-    const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024;
+    const int slots = g_shapes[ctx->shape].threads * 16;       /* per-thread best-hit records */
+    const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024 - slots;
     if ((prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
     {
         ctx->stage_bytes = prefix;
@@ -642,13 +647,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         int nb = 0;
         QR_CUDA(ctx, cudaSetDevice(d.id));
         const void *fn = (const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape);
-        if (ctx->stage_bytes != 0)
-        {
-            QR_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)ctx->stage_bytes));
-        }
+        QR_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)ctx->stage_bytes + slots));
         QR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn,
-                     g_shapes[ctx->shape].threads, ctx->stage_bytes));
+                     g_shapes[ctx->shape].threads, ctx->stage_bytes + slots));
         if (nb < 1)
         {
             return qr_fail(ctx, QR_E_CUDA, "kernel does not fit on device %d", d.id);
@@ -692,7 +694,8 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     void *args[] = { (void *)&p };
     QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
-                                  dim3(grid), dim3(threads), args, ctx->stage_bytes, d.stream));
+                                  dim3(grid), dim3(threads), args,
+                                  ctx->stage_bytes + (size_t)threads * 16u, d.stream));
     QR_CUDA(ctx, cudaGetLastError());
     QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     d.timed = true;
@@ -998,7 +1001,7 @@ extern "C" int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info)
     info->regs_per_thread = ctx->fattr.numRegs;
     info->local_bytes_per_thread = (int)ctx->fattr.localSizeBytes;
     info->smem_static_bytes = (int)ctx->fattr.sharedSizeBytes;
-    info->smem_dynamic_bytes = (int)ctx->stage_bytes;
+    info->smem_dynamic_bytes = (int)ctx->stage_bytes + g_shapes[ctx->shape].threads * 16;
     info->scene_in_smem = ctx->stage_bytes != 0;
     return QR_OK;
 }

@@ -146,6 +146,38 @@ template <> struct qr_hot<true>
 };
 #endif
 
+/*
+ * Per-thread scratch record for the best hit of a list walk (surface | side,
+ * local hit point).  The walk only WRITES it when a nearer candidate passes
+ * clipping and the shader reads it once afterwards, so on the device it
+ * lives in shared memory (one 16-byte slot per thread, one STS.128 / LDS.128)
+ * instead of five registers that every loop iteration would carry along.
+ */
+struct qr_hitrec { uint32_t so_side; float lx, ly, lz; };
+
+#if defined(__CUDA_ARCH__)
+typedef uint32_t qr_slot;               /* shared-window address of the slot */
+__device__ __forceinline__ void qr_slot_put(qr_slot s, uint32_t so_side, float lx, float ly, float lz)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(s), "r"(so_side), "f"(lx), "f"(ly), "f"(lz) : "memory");
+}
+__device__ __forceinline__ qr_hitrec qr_slot_get(qr_slot s)
+{
+    qr_hitrec r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.so_side), "=f"(r.lx), "=f"(r.ly), "=f"(r.lz) : "r"(s) : "memory");
+    return r;
+}
+#else
+typedef qr_hitrec *qr_slot;
+QR_HD void qr_slot_put(qr_slot s, uint32_t so_side, float lx, float ly, float lz)
+{
+    s->so_side = so_side; s->lx = lx; s->ly = ly; s->lz = lz;
+}
+QR_HD qr_hitrec qr_slot_get(qr_slot s) { return *s; }
+#endif
+
 template <bool SH>
 struct qr_view
 {
@@ -159,11 +191,15 @@ struct qr_view
     const uint32_t       *texels;
 };
 
-/* quad "q" of record "i" of a section with "quads" quads per record */
-#define QR_SURF(v, i, q)  qr_hot<SH>::ld((v).surf,  (uint32_t)(i) * (QR_KSURF_QUADS * 16u) + (q) * 16u)
-#define QR_SHADE(v, i, q) qr_hot<SH>::ld((v).shade, (uint32_t)(i) * (QR_KSHADE_QUADS * 16u) + (q) * 16u)
-#define QR_MAT(v, i, q)   qr_hot<SH>::ld((v).mat,   (uint32_t)(i) * (QR_KMAT_QUADS * 16u) + (q) * 16u)
-#define QR_LGT(v, i, q)   qr_hot<SH>::ld((v).lgt,   (uint32_t)(i) * (QR_KLGT_QUADS * 16u) + (q) * 16u)
+/* quad "q" of the surface record at byte offset "so" (= surface index * 128) */
+#define QR_SURF(v, so, q)  qr_hot<SH>::ld((v).surf,  (uint32_t)(so) + (q) * 16u)
+/* shading record of the same surface (32 B each) */
+#define QR_SHADE(v, so, q) qr_hot<SH>::ld((v).shade, ((uint32_t)(so) >> 2) + (q) * 16u)
+#define QR_MAT(v, i, q)    qr_hot<SH>::ld((v).mat,   (uint32_t)(i) * (QR_KMAT_QUADS * 16u) + (q) * 16u)
+#define QR_LGT(v, i, q)    qr_hot<SH>::ld((v).lgt,   (uint32_t)(i) * (QR_KLGT_QUADS * 16u) + (q) * 16u)
+
+/* surfaces are named by the byte offset of their record; "no surface": */
+#define QR_SO_NIL  0xFFFFFF80u
 
 /* host / global-memory view: "img" is the whole kscene image */
 QR_HD void qr_view_init(qr_view<false> &v, const void *img)
@@ -189,15 +225,15 @@ struct qr_counters
 /* continuation of a level that waits for a child ray */
 struct qr_frame
 {
-    float   col[3];          /* COL of the level so far */
-    float   ray[3];          /* RAY_X/Y/Z of the level */
-    float   hit[3];          /* HIT_X/Y/Z */
-    float   nrm[3];          /* NRM_X/Y/Z */
-    float   loc[3];          /* NRM_I/J/K: stored local hit (tracer.cpp:2272-2282) */
-    float   c_trn, c_rfl;    /* ctx_C_TRN / ctx_C_RFL */
-    int32_t si;              /* surface being shaded */
-    int32_t flg;             /* ctx_LOCAL(FLG): side | props */
-    int32_t stage;           /* 0: child is the refraction ray, 1: reflection */
+    float    col[3];         /* COL of the level so far */
+    float    ray[3];         /* RAY_X/Y/Z of the level */
+    float    hit[3];         /* HIT_X/Y/Z */
+    float    nrm[3];         /* NRM_X/Y/Z */
+    float    loc[3];         /* NRM_I/J/K: stored local hit (tracer.cpp:2272-2282) */
+    float    c_trn, c_rfl;   /* ctx_C_TRN / ctx_C_RFL */
+    uint32_t so;             /* surface being shaded */
+    int32_t  flg;            /* ctx_LOCAL(FLG): side | props */
+    int32_t  stage;          /* 0: child is the refraction ray, 1: reflection */
 };
 
 #define QR_MODE_CLOSEST 0
@@ -238,22 +274,19 @@ QR_HD void qr_xform(const qr_f4 q5, const qr_f4 q6, const float tck_z, uint32_t 
 }
 
 /*
- * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of surface "si"
- * (descriptor "d", first quad "q0").  (lr, ld) are the ray / diff in the
+ * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of the surface at
+ * "so" (descriptor "d", first quad "q0") that already passed the depth tests
+ * t_buf > t and t_min < t (1602-1610).  (lr, ld) are the ray / diff in the
  * surface's field set (world or trnode space).  On success lx/ly/lz hold the
  * (possibly adjusted) local hit point.
  */
 template <bool SH>
-QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
+QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0,
                    float ox, float oy, float oz, float rx, float ry, float rz,
                    float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
-                   float t_min, float t_buf, float t,
-                   bool dmask, uint32_t amask, int side,
+                   float t, bool dmask, uint32_t amask, int side,
                    float &lx, float &ly, float &lz)
 {
-    if (!qr_gt(t_buf, t)) return false;
-    if (!(t_min < t)) return false;
-
     const float hx = qr_add(qr_mul(rx, t), ox);
     const float hy = qr_add(qr_mul(ry, t), oy);
     const float hz = qr_add(qr_mul(rz, t), oz);
@@ -276,8 +309,8 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
     {
         const uint32_t conic = QR_D_CONIC(d);
         const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
-        const qr_f4 q1 = QR_SURF(v, si, 1);
-        const float t_eps = QR_SURF(v, si, 7).z;
+        const qr_f4 q1 = QR_SURF(v, so, 1);
+        const float t_eps = QR_SURF(v, so, 7).z;
         const float li = qr_pick3(iI, lx, ly, lz), lj = qr_pick3(iJ, lx, ly, lz), lk = qr_pick3(iK, lx, ly, lz);
         float a0 = qr_mul(li, li);
         if (conic != 2)
@@ -322,64 +355,60 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
         }
     }
 
-    /* axis min/max 1874-1927 */
-    bool m = true;
+    /* axis min/max 1874-1927; an axis that is switched off holds -inf / +inf
+     * (qr_kscene.h), so all six compares run unconditionally */
     if (d & QR_D_MM_MASK)
     {
-        const qr_f4 q3 = QR_SURF(v, si, 3), q4 = QR_SURF(v, si, 4);
-        if (d & (1u << 21)) m = m && (q3.x <= lx);
-        if (d & (8u << 21)) m = m && qr_ge(q4.x, lx);
-        if (d & (2u << 21)) m = m && (q3.y <= ly);
-        if (d & (16u << 21)) m = m && qr_ge(q4.y, ly);
-        if (d & (4u << 21)) m = m && (q3.z <= lz);
-        if (d & (32u << 21)) m = m && qr_ge(q4.z, lz);
+        const qr_f4 q3 = QR_SURF(v, so, 3), q4 = QR_SURF(v, so, 4);
+        const bool m = (q3.x <= lx) && (q3.y <= ly) && (q3.z <= lz)
+                    && qr_ge(q4.x, lx) && qr_ge(q4.y, ly) && qr_ge(q4.z, lz);
+        if (!m) return false;
     }
 
     if (!(d & QR_D_HASCLIP_MASK))
     {
-        return m;
+        return true;
     }
 
     /* custom clippers 1931-2151.  The reference evaluates the whole list for
      * the packet; a lone sample may stop as soon as its mask is clear and no
      * accumulator is open (a cleared mask can only come back through an
      * accum enter/leave pair). */
-    const int s_trnode = (int)qr_f2u(QR_SURF(v, si, 4).w);
-    const uint32_t c_def = qr_f2u(QR_SURF(v, si, 7).w);
+    const uint32_t s_trnode = qr_f2u(QR_SURF(v, so, 4).w);
+    const uint32_t c_def = qr_f2u(QR_SURF(v, so, 7).w);
     float nx = 0.0f, ny = 0.0f, nz = 0.0f;      /* NRM_X/Y/Z */
     float ni = 0.0f, nj = 0.0f, nk = 0.0f;      /* NRM_I/J/K */
-    bool  acc = false, in_acc = false;
-    int   redx = QR_NIL;
+    bool  m = true, acc = false, in_acc = false;
+    int32_t redx = QR_NIL;
     bool  last = true;
 
-    for (int di = (int)qr_f2u(QR_SURF(v, si, 3).w); di != QR_NIL; )
+    for (uint32_t di = qr_f2u(QR_SURF(v, so, 3).w); ; di++)
     {
+        const qr_kelem ce = v.elems[di];
+        if (ce.w == QR_KEND) break;
         if (!m && !in_acc)
         {
             return false;
         }
-        const qr_kelem ce = v.elems[di];
-        const int cur = di;
-        di = ce.next;
 
-        if (ce.simd == QR_NIL)
+        if (ce.w & QR_KC_ACCUM)
         {
-            if (ce.op > 0)
-            {
-                m = !m && acc;                  /* annpx: ~mask & C_ACC */
-                in_acc = false;
-            }
-            else
+            if (ce.w & QR_KC_NEG)
             {
                 acc = m;
                 m = c_def != 0;
                 in_acc = true;
             }
+            else
+            {
+                m = !m && acc;                  /* annpx: ~mask & C_ACC */
+                in_acc = false;
+            }
             continue;
         }
 
-        const int ci = ce.simd;
-        const qr_f4 c0 = QR_SURF(v, ci, 0);
+        const uint32_t co = QR_K_SURF_OFF(ce.w);
+        const qr_f4 c0 = QR_SURF(v, co, 0);
         const uint32_t cd = qr_f2u(c0.w);
         bool have_local = false;
 
@@ -390,12 +419,12 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
                 ni = qr_sub(nx, c0.x);
                 nj = qr_sub(ny, c0.y);
                 nk = qr_sub(nz, c0.z);
-                if (cur == redx) redx = QR_NIL;
+                if ((int32_t)di == redx) redx = QR_NIL;
                 have_local = true;
             }
         }
         else
-        if (ci == s_trnode)
+        if (co == s_trnode)
         {
             nx = qr_add(lx, q0.x);
             ny = qr_add(ly, q0.y);
@@ -412,7 +441,7 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
             if (cd & QR_D_TRM_MASK)
             {
                 float o4, o5, o6;
-                qr_xform(QR_SURF(v, ci, 5), QR_SURF(v, ci, 6), QR_SURF(v, ci, 7).x, QR_D_TRM(cd),
+                qr_xform(QR_SURF(v, co, 5), QR_SURF(v, co, 6), QR_SURF(v, co, 7).x, QR_D_TRM(cd),
                          nx, ny, nz, o4, o5, o6);
                 if (cd & QR_D_ARRAY_MASK)
                 {
@@ -437,13 +466,13 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
             }
             else
             {
-                const qr_f4 c1 = QR_SURF(v, ci, 1);
+                const qr_f4 c1 = QR_SURF(v, co, 1);
                 float a4 = qr_mul(qr_mul(p0, p0), c1.x);
                 float a5 = qr_mul(qr_mul(p1, p1), c1.y);
                 float a6 = qr_mul(qr_mul(p2, p2), c1.z);
                 if (ctag == 2)
                 {
-                    const qr_f4 c2 = QR_SURF(v, ci, 2);
+                    const qr_f4 c2 = QR_SURF(v, co, 2);
                     a4 = qr_sub(a4, qr_mul(qr_add(c2.x, c2.x), p0));
                     a5 = qr_sub(a5, qr_mul(qr_add(c2.y, c2.y), p1));
                     a6 = qr_sub(a6, qr_mul(qr_add(c2.z, c2.z), p2));
@@ -453,7 +482,7 @@ QR_HD bool qr_clip(const qr_view<SH> &v, int si, uint32_t d, const qr_f4 q0,
                 val = qr_add(a4, a6);
             }
             /* APPLY_CLIP 488-496 */
-            last = ce.op < 0 ? qr_ge(val, 0.0f) : (val <= 0.0f);
+            last = (ce.w & QR_KC_NEG) ? qr_ge(val, 0.0f) : (val <= 0.0f);
         }
         m = m && last;
     }
@@ -478,293 +507,317 @@ QR_HD uint32_t qr_side_props(uint32_t packed, int side)
 
 /*
  * One list walk, OO_cyc 1341 .. OO_out 5142, for one sample.
- *   mode CLOSEST: returns true when something was hit; t_buf / best_* updated
+ *   mode CLOSEST: returns true when something was hit; t_buf and *best updated
  *   mode SHADOW : returns true when the sample is in shadow (first occluder)
  * (plx, ply, plz) is the stored local hit of the originating level (NRM_I/J/K
- * of the previous context), used when the ray starts on the surface tested.
+ * of the previous context), used when the ray starts on the surface tested
+ * (p_obj, tracer.cpp:1352-1373).
  *
- * Transform caching (tracer.cpp:1377-1421, 1483-1500): while a transform node
- * (array with a matrix) is open, (tdx,tdy,tdz) is the ray origin and
- * (cr0,cr1,cr2) the ray direction in the node's space; outside, (cr0..) is the
- * world ray.  Which elements run inside a node is compiled into e.op.
+ * (bo, cr) are the ray origin and direction in the CURRENT frame: the world,
+ * or the space of the open transform node (transform caching, tracer.cpp:
+ * 1377-1421, 1483-1500), or for one element the space of a surface with its
+ * own matrix.  Which elements open / close a frame is compiled into the
+ * element flags (qr_kscene.h).  Elements are sequential, so the successor is
+ * loaded while the current one is processed; a bounding-volume element also
+ * loads its skip target up front.
  */
 template <bool SH>
-QR_HD bool qr_walk(const qr_view<SH> &v, int head, int mode,
+QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                    float ox, float oy, float oz, float rx, float ry, float rz,
-                   float t_min, float t_max, int p_obj, int p_flg,
+                   float t_min, float t_max, uint32_t p_obj, int p_flg,
                    float plx, float ply, float plz,
-                   float &t_buf, int &best_si, int &best_side,
-                   float &blx, float &bly, float &blz)
+                   float &t_buf, qr_slot best)
 {
-    float tdx = 0.0f, tdy = 0.0f, tdz = 0.0f;   /* DFF_X/Y/Z of the open trnode */
-    float cr0 = rx, cr1 = ry, cr2 = rz;         /* RAY_X/Y/Z, or RAY_I/J/K of the open trnode */
+    float bo0 = ox, bo1 = oy, bo2 = oz;
+    float cr0 = rx, cr1 = ry, cr2 = rz;
+    const int  pf = p_flg & (QR_FLAG_SIDE | QR_FLAG_PASS);
+    /* a root t <= 0 (or NaN) can never pass t_min < t when t_min >= 0 */
+    const bool no_neg = !(t_min < 0.0f);
 
     t_buf = t_max;
-    best_si = QR_NIL;
-    best_side = 0;
+    bool found = false;
 
-    int ei = head;
-    while (ei != QR_NIL)
+    uint32_t ei = head;
+    qr_kelem e = v.elems[ei];
+
+    for (;;)
     {
-        const qr_kelem e = v.elems[ei];
-        ei = e.next;
-
-        const int si = e.simd;
-        const uint32_t op = (uint32_t)e.op;
-        const qr_f4 q0 = QR_SURF(v, si, 0);
-        const uint32_t d = qr_f2u(q0.w);
-        const bool same = (si == p_obj);
-
-        /* ---- object prologue, OO_ini .. OO_trm 1348-1558 ---- */
-        if (op & QR_OP_OPEN)
+        const uint32_t w = e.w;
+        const uint32_t kind = QR_K_KIND(w);
+        if (kind >= QR_K_JUMP)
         {
-            /* array with a matrix: transform origin diff and ray once for the
-             * elements up to the node's last one (1483-1496) */
-            const qr_f4 q5 = QR_SURF(v, si, 5), q6 = QR_SURF(v, si, 6);
-            const float tckz = QR_SURF(v, si, 7).x;
-            qr_xform(q5, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
-                     tdx, tdy, tdz);
-            qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
-            continue;                           /* srf_t[0] == 0: nothing to intersect */
+            if (kind == QR_K_END) break;
+            ei = (uint32_t)e.aux;
+            e = v.elems[ei];
+            continue;
         }
 
-        float ld0, ld1, ld2;                    /* DFF in the surface's field set */
-        float lr0 = cr0, lr1 = cr1, lr2 = cr2;  /* RAY in the surface's field set */
+        uint32_t ni = ei + 1;
+        qr_kelem en = v.elems[ni];              /* successor, in flight during this element */
 
-        if (same)
+        do
         {
-            /* 1352-1373: secondary ray leaving this very surface reuses the
-             * stored local hit as its local diff */
-            ld0 = plx; ld1 = ply; ld2 = plz;
-            if (op & QR_OP_OWNTRM)
+            if (kind == QR_K_NOP) break;
+
+            const uint32_t so = QR_K_SURF_OFF(w);
+            const qr_f4 q0 = QR_SURF(v, so, 0);
+            const uint32_t d = qr_f2u(q0.w);
+
+            if (kind == QR_K_OPEN)
             {
-                qr_xform(QR_SURF(v, si, 5), QR_SURF(v, si, 6), QR_SURF(v, si, 7).x, QR_D_TRM(d),
-                         rx, ry, rz, lr0, lr1, lr2);
+                /* array with a matrix: transform origin diff and ray once for
+                 * the elements up to the node's last one (1483-1496) */
+                const qr_f4 q5 = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
+                const float tckz = QR_SURF(v, so, 7).x;
+                qr_xform(q5, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                         bo0, bo1, bo2);
+                qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
+                break;
             }
-        }
-        else
-        if (op & QR_OP_CACHED)
-        {
-            /* 1385-1406: child of the open trnode */
-            ld0 = qr_sub(tdx, q0.x);
-            ld1 = qr_sub(tdy, q0.y);
-            ld2 = qr_sub(tdz, q0.z);
-        }
-        else
-        {
-            /* OO_dff 1429-1556 */
-            ld0 = qr_sub(ox, q0.x);
-            ld1 = qr_sub(oy, q0.y);
-            ld2 = qr_sub(oz, q0.z);
-            if (op & QR_OP_OWNTRM)
+
+            if (kind == QR_K_BV)
             {
-                const qr_f4 q5 = QR_SURF(v, si, 5), q6 = QR_SURF(v, si, 6);
-                const float tckz = QR_SURF(v, si, 7).x;
-                qr_xform(q5, q6, tckz, QR_D_TRM(d), ld0, ld1, ld2, ld0, ld1, ld2);
-                qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, lr0, lr1, lr2);
-            }
-        }
-        if (op & QR_OP_CLOSE)
-        {
-            cr0 = rx; cr1 = ry; cr2 = rz;       /* last element of the open trnode */
-        }
+                /* AR_ptr 3955-4054: bounding volume of an array */
+                const qr_kelem ea = v.elems[(uint32_t)e.aux];
+                const qr_f4 q1 = QR_SURF(v, so, 1);
+                const float ld0 = qr_sub(bo0, q0.x), ld1 = qr_sub(bo1, q0.y), ld2 = qr_sub(bo2, q0.z);
+                float x1 = cr0;
+                float x0 = qr_mul(q1.x, x1);
+                float x5 = ld0;
+                float q7 = qr_mul(q1.x, x5);
+                float x3 = x1;
+                x1 = qr_mul(x1, x0); x3 = qr_mul(x3, q7); x5 = qr_mul(x5, q7);
 
-        /* AR_ptr 3955-4054: bounding volume of an array */
-        if (op & QR_OP_BV)
-        {
-            const qr_f4 q1 = QR_SURF(v, si, 1);
-            float x1 = lr0;
-            float x0 = qr_mul(q1.x, x1);
-            float x5 = ld0;
-            float q7 = qr_mul(q1.x, x5);
-            float x3 = x1;
-            x1 = qr_mul(x1, x0); x3 = qr_mul(x3, q7); x5 = qr_mul(x5, q7);
+                float x2 = cr1;
+                x0 = qr_mul(q1.y, x2);
+                float x6 = ld1;
+                q7 = qr_mul(q1.y, x6);
+                float x4 = x2;
+                x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
+                x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
 
-            float x2 = lr1;
-            x0 = qr_mul(q1.y, x2);
-            float x6 = ld1;
-            q7 = qr_mul(q1.y, x6);
-            float x4 = x2;
-            x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
-            x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
+                x2 = cr2;
+                x0 = qr_mul(q1.z, x2);
+                x6 = ld2;
+                q7 = qr_mul(q1.z, x6);
+                x4 = x2;
+                x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
+                x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
 
-            x2 = lr2;
-            x0 = qr_mul(q1.z, x2);
-            x6 = ld2;
-            q7 = qr_mul(q1.z, x6);
-            x4 = x2;
-            x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
-            x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
-
-            x5 = qr_sub(x5, q1.w);
-            x5 = qr_mul(x5, x1);
-            x3 = qr_mul(x3, x3);
-            x3 = qr_sub(x3, x5);
-            if (!(0.0f <= x3))
-            {
-                /* AR_skp: continue behind the array's last leaf */
-                ei = e.aux;
-                if (op & QR_OP_SKIPCLOSE)
+                x5 = qr_sub(x5, q1.w);
+                x5 = qr_mul(x5, x1);
+                x3 = qr_mul(x3, x3);
+                x3 = qr_sub(x3, x5);
+                if (!(0.0f <= x3))
                 {
-                    cr0 = rx; cr1 = ry; cr2 = rz;
+                    /* AR_skp: continue behind the array's last leaf */
+                    ni = (uint32_t)e.aux;
+                    en = ea;
+                    if (w & QR_KF_SKIPCLOSE)
+                    {
+                        bo0 = ox; bo1 = oy; bo2 = oz;
+                        cr0 = rx; cr1 = ry; cr2 = rz;
+                    }
                 }
+                break;
             }
-            continue;
-        }
 
-        const uint32_t tag = QR_D_TAG(d);
-        if (tag == 0) continue;
+            const bool same = (so == p_obj);
+            float ld0, ld1, ld2;
 
-        float lx, ly, lz;
-
-        if (tag == 1)
-        {
-            /* PL_ptr 4062-4136 */
-            if (same) continue;
-            const uint32_t k = QR_D_MAP(d, 2), sg = QR_D_SGN(d, 2);
-            const float dk = qr_neg(qr_sgn(qr_pick3(k, ld0, ld1, ld2), sg));
-            const float rk = qr_sgn(qr_pick3(k, lr0, lr1, lr2), sg);
-            if (!(0.0f != rk)) continue;
-            const float t = qr_div(dk, rk);
-            if (!qr_clip<SH>(v, si, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
-                             t_min, t_buf, t, false, 0u, 0, lx, ly, lz)) continue;
-            const int side = (rk < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
-            if (mode == QR_MODE_SHADOW)
+            if (w & QR_KF_OWNTRM)
             {
-                if (qr_casts_shadow(qr_side_props(qr_f2u(QR_SURF(v, si, 2).w), side))) return true;
-                continue;
-            }
-            t_buf = t; best_si = si; best_side = side;
-            blx = lx; bly = ly; blz = lz;
-            continue;
-        }
-
-        float a_val, b_val, c_val, d_val;
-        const qr_f4 q1 = QR_SURF(v, si, 1);
-        const qr_f4 q2 = QR_SURF(v, si, 2);
-
-        if (tag == 3)
-        {
-            /* TP_ptr 4216-4277 */
-            const uint32_t iI = QR_D_MAP(d, 0), iK = QR_D_MAP(d, 2);
-            const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
-            const float ri = qr_pick3(iI, lr0, lr1, lr2), di = qr_pick3(iI, ld0, ld1, ld2);
-            const float rk = qr_pick3(iK, lr0, lr1, lr2), dk = qr_pick3(iK, ld0, ld1, ld2);
-            float a5 = qr_sub(qr_mul(di, rk), qr_mul(dk, ri));
-            a5 = qr_mul(a5, a5);
-            a5 = qr_mul(a5, sci_i);
-            a5 = qr_mul(a5, sci_k);
-            d_val = qr_abs(a5);
-            b_val = qr_add(qr_mul(qr_mul(sci_i, di), ri), qr_mul(qr_mul(sci_k, dk), rk));
-            c_val = qr_add(qr_mul(qr_mul(di, di), sci_i), qr_mul(qr_mul(dk, dk), sci_k));
-            a_val = qr_add(qr_mul(qr_mul(ri, ri), sci_i), qr_mul(qr_mul(rk, rk), sci_k));
-        }
-        else
-        {
-            /* QD_ptr 4378-4447 */
-            float a7 = qr_sub(qr_mul(q1.x, ld0), q2.x);
-            float a3 = qr_mul(lr0, a7);
-            float a1 = qr_mul(lr0, qr_mul(q1.x, lr0));
-            a7 = qr_sub(a7, q2.x);
-            float a5 = qr_mul(ld0, a7);
-
-            a7 = qr_sub(qr_mul(q1.y, ld1), q2.y);
-            float a4 = qr_mul(lr1, a7);
-            float a2 = qr_mul(lr1, qr_mul(q1.y, lr1));
-            a7 = qr_sub(a7, q2.y);
-            float a6 = qr_mul(ld1, a7);
-
-            a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
-
-            a7 = qr_sub(qr_mul(q1.z, ld2), q2.z);
-            a4 = qr_mul(lr2, a7);
-            a2 = qr_mul(lr2, qr_mul(q1.z, lr2));
-            a7 = qr_sub(a7, q2.z);
-            a6 = qr_mul(ld2, a7);
-
-            a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
-
-            a5 = qr_sub(a5, q1.w);
-            a_val = a1;
-            b_val = a3;
-            c_val = a5;
-            d_val = qr_sub(qr_mul(a3, a3), qr_mul(a5, a1));
-        }
-
-        /* QD_rts 4449-4547 */
-        if (!(0.0f <= d_val)) continue;
-        const qr_f4 q7 = QR_SURF(v, si, 7);
-        const float b = qr_neg(b_val);
-        const bool dmask = d_val < q7.y;
-        const float sd = qr_u2f(qr_f2u(qr_sqrt(d_val)) ^ (qr_f2u(b) & 0x80000000u));
-        const float bd = qr_add(b, sd);
-        const bool m_pos = 0.0f <= sd;
-        float t1n = m_pos ? c_val : bd;
-        float t1d = m_pos ? bd : a_val;
-        float t2n = m_pos ? bd : c_val;
-        float t2d = m_pos ? a_val : bd;
-        const uint32_t amask = qr_f2u(a_val) & 0x80000000u;
-        float t1 = 0.0f, t2 = 0.0f;
-        bool k1 = true, k2 = true;
-
-        if (dmask)
-        {
-            /* 4572-4623: near-zero determinant, both roots up front */
-            if (t1n == 0.0f) t1d = 1.0f;
-            if (t2n == 0.0f) t2d = 1.0f;
-            t1 = qr_div(t1n, t1d);
-            t2 = qr_div(t2n, t2d);
-            k1 = t1d != 0.0f;
-            k2 = t2d != 0.0f;
-            float a2 = qr_u2f(qr_f2u(qr_sub(t1, t2)) ^ amask);
-            const bool fm = 0.0f <= a2;
-            a2 = fm ? a2 : 0.0f;
-            const float a5 = qr_abs(qr_mul(fm ? q7.z : 0.0f, t1));
-            a2 = qr_sub(qr_mul(a2, -0.5f), a5);
-            uint32_t u2 = qr_f2u(a2) ^ amask;
-            if (!(k1 && k2)) u2 = 0;
-            t1 = qr_add(t1, qr_u2f(u2));
-            t2 = qr_sub(t2, qr_u2f(u2));
-        }
-
-        /* QD_srt 4646-4824, one lane: the side tried first follows the sign of
-         * "a"; a hit on the first side ends the surface (overdraw check) */
-        const int first = qr_gt(0.0f, a_val) ? QR_FLAG_SIDE_INNER : QR_FLAG_SIDE_OUTER;
-        const int pf = p_flg & (QR_FLAG_SIDE | QR_FLAG_PASS);
-#pragma unroll 1
-        for (int pass = 0; pass < 2; pass++)
-        {
-            const int side = pass == 0 ? first : (first ^ 1);
-            /* CHECK_SIDE 531-540 */
-            if (same && (pf == 1 - side || pf == 2 + side)) continue;
-            float t; bool k;
-            if (dmask)
-            {
-                t = side == QR_FLAG_SIDE_OUTER ? t1 : t2;
-                k = side == QR_FLAG_SIDE_OUTER ? k1 : k2;
+                /* OO_dff 1429-1556: surface with its own matrix */
+                const qr_f4 q5t = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
+                const float tckz = QR_SURF(v, so, 7).x;
+                qr_xform(q5t, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
+                if (!same)
+                {
+                    qr_xform(q5t, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                             ld0, ld1, ld2);
+                }
             }
             else
             {
-                const float nn = side == QR_FLAG_SIDE_OUTER ? t1n : t2n;
-                const float dd = side == QR_FLAG_SIDE_OUTER ? t1d : t2d;
-                t = qr_div(nn, dd);
-                k = dd != 0.0f;
+                ld0 = qr_sub(bo0, q0.x);
+                ld1 = qr_sub(bo1, q0.y);
+                ld2 = qr_sub(bo2, q0.z);
             }
-            if (!k) continue;
-            if (!qr_clip<SH>(v, si, d, q0, ox, oy, oz, rx, ry, rz, lr0, lr1, lr2, ld0, ld1, ld2,
-                             t_min, t_buf, t, dmask, amask, side, lx, ly, lz)) continue;
-            if (mode == QR_MODE_SHADOW)
+            if (same)
             {
-                if (qr_casts_shadow(qr_side_props(qr_f2u(q2.w), side))) return true;
+                /* 1352-1373: secondary ray leaving this very surface reuses the
+                 * stored local hit as its local diff */
+                ld0 = plx; ld1 = ply; ld2 = plz;
+            }
+
+            /* candidate roots, tried in the order (first, first ^ 1) */
+            float t1n, t1d, t2n, t2d;           /* lazily divided roots (outer, inner) */
+            float t1 = 0.0f, t2 = 0.0f;         /* roots when "ready" */
+            bool  k1 = true, k2 = true, ready, dmask = false;
+            uint32_t amask = 0;
+            int   first, npass;
+
+            if (kind == QR_K_PLANE)
+            {
+                /* PL_ptr 4062-4136 */
+                if (same) break;
+                const uint32_t k = QR_D_MAP(d, 2);
+                const uint32_t sg = (d << (31 - 14)) & 0x80000000u;     /* a_sgn[K] */
+                const uint32_t dk = (qr_f2u(qr_pick3(k, ld0, ld1, ld2)) ^ sg) ^ 0x80000000u;
+                const uint32_t rk = qr_f2u(qr_pick3(k, cr0, cr1, cr2)) ^ sg;
+                if (!(0.0f != qr_u2f(rk))) break;
+                if (no_neg && (int32_t)(dk ^ rk) < 0) break;
+                t1 = t2 = qr_div(qr_u2f(dk), qr_u2f(rk));
+                first = (qr_u2f(rk) < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
+                npass = 1;
+                ready = true;
+                t1n = t1d = t2n = t2d = 0.0f;
+            }
+            else
+            {
+                float a_val, b_val, c_val, d_val;
+                const qr_f4 q1 = QR_SURF(v, so, 1);
+
+                if (kind == QR_K_TWOPLANE)
+                {
+                    /* TP_ptr 4216-4277 */
+                    const uint32_t iI = QR_D_MAP(d, 0), iK = QR_D_MAP(d, 2);
+                    const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
+                    const float ri = qr_pick3(iI, cr0, cr1, cr2), di = qr_pick3(iI, ld0, ld1, ld2);
+                    const float rk = qr_pick3(iK, cr0, cr1, cr2), dk = qr_pick3(iK, ld0, ld1, ld2);
+                    float a5 = qr_sub(qr_mul(di, rk), qr_mul(dk, ri));
+                    a5 = qr_mul(a5, a5);
+                    a5 = qr_mul(a5, sci_i);
+                    a5 = qr_mul(a5, sci_k);
+                    d_val = qr_abs(a5);
+                    b_val = qr_add(qr_mul(qr_mul(sci_i, di), ri), qr_mul(qr_mul(sci_k, dk), rk));
+                    c_val = qr_add(qr_mul(qr_mul(di, di), sci_i), qr_mul(qr_mul(dk, dk), sci_k));
+                    a_val = qr_add(qr_mul(qr_mul(ri, ri), sci_i), qr_mul(qr_mul(rk, rk), sci_k));
+                }
+                else
+                {
+                    /* QD_ptr 4378-4447 */
+                    const qr_f4 q2 = QR_SURF(v, so, 2);
+                    float a7 = qr_sub(qr_mul(q1.x, ld0), q2.x);
+                    float a3 = qr_mul(cr0, a7);
+                    float a1 = qr_mul(cr0, qr_mul(q1.x, cr0));
+                    a7 = qr_sub(a7, q2.x);
+                    float a5 = qr_mul(ld0, a7);
+
+                    a7 = qr_sub(qr_mul(q1.y, ld1), q2.y);
+                    float a4 = qr_mul(cr1, a7);
+                    float a2 = qr_mul(cr1, qr_mul(q1.y, cr1));
+                    a7 = qr_sub(a7, q2.y);
+                    float a6 = qr_mul(ld1, a7);
+
+                    a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
+
+                    a7 = qr_sub(qr_mul(q1.z, ld2), q2.z);
+                    a4 = qr_mul(cr2, a7);
+                    a2 = qr_mul(cr2, qr_mul(q1.z, cr2));
+                    a7 = qr_sub(a7, q2.z);
+                    a6 = qr_mul(ld2, a7);
+
+                    a1 = qr_add(a1, a2); a3 = qr_add(a3, a4); a5 = qr_add(a5, a6);
+
+                    a5 = qr_sub(a5, q1.w);
+                    a_val = a1;
+                    b_val = a3;
+                    c_val = a5;
+                    d_val = qr_sub(qr_mul(a3, a3), qr_mul(a5, a1));
+                }
+
+                /* QD_rts 4449-4547 */
+                if (!(0.0f <= d_val)) break;
+                const qr_f4 q7 = QR_SURF(v, so, 7);
+                const float b = qr_neg(b_val);
+                dmask = d_val < q7.y;
+                const float sd = qr_u2f(qr_f2u(qr_sqrt(d_val)) ^ (qr_f2u(b) & 0x80000000u));
+                const float bd = qr_add(b, sd);
+                const bool m_pos = 0.0f <= sd;
+                t1n = m_pos ? c_val : bd;
+                t1d = m_pos ? bd : a_val;
+                t2n = m_pos ? bd : c_val;
+                t2d = m_pos ? a_val : bd;
+                amask = qr_f2u(a_val) & 0x80000000u;
+                ready = dmask;
+
+                if (dmask)
+                {
+                    /* 4572-4623: near-zero determinant, both roots up front */
+                    if (t1n == 0.0f) t1d = 1.0f;
+                    if (t2n == 0.0f) t2d = 1.0f;
+                    t1 = qr_div(t1n, t1d);
+                    t2 = qr_div(t2n, t2d);
+                    k1 = t1d != 0.0f;
+                    k2 = t2d != 0.0f;
+                    float a2 = qr_u2f(qr_f2u(qr_sub(t1, t2)) ^ amask);
+                    const bool fm = 0.0f <= a2;
+                    a2 = fm ? a2 : 0.0f;
+                    const float a5 = qr_abs(qr_mul(fm ? q7.z : 0.0f, t1));
+                    a2 = qr_sub(qr_mul(a2, -0.5f), a5);
+                    uint32_t u2 = qr_f2u(a2) ^ amask;
+                    if (!(k1 && k2)) u2 = 0;
+                    t1 = qr_add(t1, qr_u2f(u2));
+                    t2 = qr_sub(t2, qr_u2f(u2));
+                }
+
+                /* QD_srt 4646-4824, one lane: the side tried first follows the
+                 * sign of "a"; a hit on the first side ends the surface */
+                first = qr_gt(0.0f, a_val) ? QR_FLAG_SIDE_INNER : QR_FLAG_SIDE_OUTER;
+                npass = 2;
+            }
+
+#pragma unroll 1
+            for (int pass = 0; pass < npass; pass++)
+            {
+                const int side = first ^ pass;
+                /* CHECK_SIDE 531-540 */
+                if (same && (pf == 1 - side || pf == 2 + side)) continue;
+                float t; bool k;
+                if (ready)
+                {
+                    t = side == QR_FLAG_SIDE_OUTER ? t1 : t2;
+                    k = side == QR_FLAG_SIDE_OUTER ? k1 : k2;
+                }
+                else
+                {
+                    const float nn = side == QR_FLAG_SIDE_OUTER ? t1n : t2n;
+                    const float dd = side == QR_FLAG_SIDE_OUTER ? t1d : t2d;
+                    t = qr_div(nn, dd);
+                    k = dd != 0.0f;
+                }
+                if (!k) continue;
+                /* CC_clp 1602-1610: depth tests */
+                if (!qr_gt(t_buf, t)) continue;
+                if (!(t_min < t)) continue;
+                float lx, ly, lz;
+                if (!qr_clip<SH>(v, so, d, q0, ox, oy, oz, rx, ry, rz, cr0, cr1, cr2, ld0, ld1, ld2,
+                                 t, dmask, amask, side, lx, ly, lz)) continue;
+                if (mode == QR_MODE_SHADOW)
+                {
+                    if (qr_casts_shadow(qr_side_props(qr_f2u(QR_SURF(v, so, 2).w), side))) return true;
+                    break;
+                }
+                t_buf = t;
+                found = true;
+                qr_slot_put(best, so | (uint32_t)side, lx, ly, lz);
                 break;
             }
-            t_buf = t; best_si = si; best_side = side;
-            blx = lx; bly = ly; blz = lz;
-            break;
         }
+        while (0);
+
+        if (w & (QR_KF_CLOSE | QR_KF_OWNTRM))
+        {
+            /* last element of the open transform node / own matrix: back to the world */
+            bo0 = ox; bo1 = oy; bo2 = oz;
+            cr0 = rx; cr1 = ry; cr2 = rz;
+        }
+        ei = ni;
+        e = en;
     }
 
-    return mode == QR_MODE_SHADOW ? false : best_si != QR_NIL;
+    return mode == QR_MODE_SHADOW ? false : found;
 }
 
 /* texel -> linear colour, PAINT_COLX 664-673 */
@@ -850,7 +903,7 @@ QR_HD float qr_fresnel(float c, float rfr, float x0, float x7)
  */
 template <bool SH>
 QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
-                           qr_frame *stack, float &out_r, float &out_g, float &out_b,
+                           qr_frame *stack, qr_slot best, float &out_r, float &out_g, float &out_b,
                            float &out_t, qr_counters &cnt)
 {
     const qr_blob_header &h = *v.h;
@@ -858,7 +911,8 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
     /* current ray */
     float ox, oy, oz, rx, ry, rz;
     float t_min, t_max;
-    int   head, mode, p_obj, p_flg;
+    uint32_t head, p_obj;
+    int   mode, p_flg;
     int   lvl = 0;
 
     /* shading state of the current level */
@@ -867,10 +921,11 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
     float tr = 0, tg = 0, tb = 0, cr = 0, cg = 0, cb = 0;
     float dot = 0.0f, c_trn = 0.0f, c_rfl = 0.0f;
     float xr = 0, xg = 0, xb = 0;
-    int   cur_si = QR_NIL, l_flg = 0, li = QR_NIL;
+    uint32_t cur_so = QR_SO_NIL, li = 0;
+    int   l_flg = 0;
 
     /* walk results */
-    float t_buf; int best_si, best_side; float blx = 0, bly = 0, blz = 0;
+    float t_buf;
 
     /* 1287-1322: primary ray; hor_i / ver_i are exact integers */
     {
@@ -886,9 +941,9 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         t_max = h.cam_t_max;
         int tx = px / h.tile_w;
         if (tx >= h.tls_row) tx = h.tls_row - 1;
-        head = v.tiles[(py / h.tile_h) * h.tls_row + tx];
+        head = (uint32_t)v.tiles[(py / h.tile_h) * h.tls_row + tx];
         mode = QR_MODE_CLOSEST;
-        p_obj = QR_NIL;
+        p_obj = QR_SO_NIL;
         p_flg = (int)h.ctx_flags;
     }
 
@@ -905,7 +960,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         }
         const bool res = qr_walk<SH>(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
                                  p_obj, p_flg, plx, ply, plz,
-                                 t_buf, best_si, best_side, blx, bly, blz);
+                                 t_buf, best);
         bool lights_phase = false;
         resume = 0;
 
@@ -915,8 +970,8 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
             const qr_kelem le = v.elems[li];
             if (!res)
             {
-                const qr_f4 l1 = QR_LGT(v, le.simd, 1), l2 = QR_LGT(v, le.simd, 2);
-                const qr_f4 sh0 = QR_SHADE(v, cur_si, 0);
+                const qr_f4 l1 = QR_LGT(v, le.w, 1), l2 = QR_LGT(v, le.w, 2);
+                const qr_f4 sh0 = QR_SHADE(v, cur_so, 0);
                 const int mi = (int)qr_f2u((l_flg & 1) ? sh0.y : sh0.x);
                 const qr_f4 m2 = QR_MAT(v, mi, 2);
                 const uint32_t props = (uint32_t)l_flg;
@@ -993,7 +1048,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     cb = qr_add(qr_mul(qr_mul(tb, l1.z), dd), cb);
                 }
             }
-            li = le.next;
+            li = li + 1;
             lights_phase = true;
         }
         else
@@ -1009,20 +1064,21 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
             else
             {
                 /* ---------------- SHADE ---------------- */
-                cur_si = best_si;
-                const qr_f4 q1 = QR_SURF(v, cur_si, 1), q2 = QR_SURF(v, cur_si, 2);
-                const uint32_t d = qr_f2u(QR_SURF(v, cur_si, 0).w);
-                const int side = best_side;
+                const qr_hitrec hr = qr_slot_get(best);
+                cur_so = hr.so_side & ~127u;
+                const qr_f4 q1 = QR_SURF(v, cur_so, 1), q2 = QR_SURF(v, cur_so, 2);
+                const uint32_t d = qr_f2u(QR_SURF(v, cur_so, 0).w);
+                const int side = (int)(hr.so_side & 1u);
                 const uint32_t props = (uint32_t)side | qr_side_props(qr_f2u(q2.w), side);   /* FETCH_PROP */
                 l_flg = (int)props;
-                const qr_f4 s0 = QR_SHADE(v, cur_si, 0);
+                const qr_f4 s0 = QR_SHADE(v, cur_so, 0);
                 const int mi = (int)qr_f2u(side ? s0.y : s0.x);
 
                 lrx = rx; lry = ry; lrz = rz;
                 hx = qr_add(qr_mul(rx, t_buf), ox);
                 hy = qr_add(qr_mul(ry, t_buf), oy);
                 hz = qr_add(qr_mul(rz, t_buf), oz);
-                lcx = blx; lcy = bly; lcz = blz;
+                lcx = hr.lx; lcy = hr.ly; lcz = hr.lz;
 
                 const uint32_t kind = QR_D_TAG(d) == 1 ? 1u : QR_D_KIND(d);
                 float tex_u = 0.0f, tex_v = 0.0f;
@@ -1071,7 +1127,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     if (d & QR_D_TRM_MASK)
                     {
                         /* MT_nrm 2184-2259: transposed matrix of the trnode */
-                        const int ti = (int)qr_f2u(QR_SURF(v, cur_si, 4).w);
+                        const uint32_t ti = qr_f2u(QR_SURF(v, cur_so, 4).w);
                         const qr_f4 t5 = QR_SURF(v, ti, 5), t6 = QR_SURF(v, ti, 6);
                         const float tck_z = QR_SURF(v, ti, 7).x;
                         const uint32_t ttrm = QR_D_TRM(qr_f2u(QR_SURF(v, ti, 0).w));
@@ -1131,7 +1187,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 {
                     /* LT_set 3164-3177 */
                     cr = tr; cg = tg; cb = tb;
-                    li = QR_NIL;
+                    li = 0;
                 }
                 else
                 {
@@ -1139,7 +1195,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     cr = qr_mul(tr, h.amb[0]);
                     cg = qr_mul(tg, h.amb[1]);
                     cb = qr_mul(tb, h.amb[2]);
-                    li = (int)qr_f2u(side ? s0.w : s0.z);
+                    li = qr_f2u(side ? s0.w : s0.z);
                 }
                 lights_phase = true;
             }
@@ -1149,10 +1205,11 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         {
             /* LT_cyc 2762-2831: next light that sees the front of the surface */
             bool go_shadow = false;
-            while (li != QR_NIL)
+            for (;;)
             {
                 const qr_kelem le = v.elems[li];
-                const qr_f4 l0 = QR_LGT(v, le.simd, 0);
+                if (le.w == QR_KEND) break;
+                const qr_f4 l0 = QR_LGT(v, le.w, 0);
                 const float x1 = qr_sub(l0.x, hx);
                 const float x2 = qr_sub(l0.y, hy);
                 const float x3 = qr_sub(l0.z, hz);
@@ -1166,15 +1223,15 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     rx = x1; ry = x2; rz = x3;
                     t_min = 0.0f;
                     t_max = l0.w;
-                    head = le.aux;
+                    head = (uint32_t)le.aux;
                     mode = QR_MODE_SHADOW;
-                    p_obj = cur_si;
+                    p_obj = cur_so;
                     p_flg = l_flg | QR_FLAG_PASS_BACK | QR_FLAG_SHAD;
                     cnt.shadow++;
                     go_shadow = true;
                     break;
                 }
-                li = le.next;
+                li = li + 1;
             }
             if (go_shadow) continue;
             resume = 0;
@@ -1197,7 +1254,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 nx = f.nrm[0]; ny = f.nrm[1]; nz = f.nrm[2];
                 lcx = f.loc[0]; lcy = f.loc[1]; lcz = f.loc[2];
                 c_trn = f.c_trn; c_rfl = f.c_rfl;
-                cur_si = f.si; l_flg = f.flg;
+                cur_so = f.so; l_flg = f.flg;
                 if (f.stage == 0)
                 {
                     /* TR_ret 3534-3552 */
@@ -1214,15 +1271,16 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
 
             const int side = l_flg & 1;
             const uint32_t props = (uint32_t)l_flg;
-            const qr_f4 s0 = QR_SHADE(v, cur_si, 0);
-            const qr_f4 s1 = QR_SHADE(v, cur_si, 1);
+            const qr_f4 s0 = QR_SHADE(v, cur_so, 0);
+            const qr_f4 s1 = QR_SHADE(v, cur_so, 1);
             const int mi = (int)qr_f2u(side ? s0.y : s0.x);
             const qr_f4 m3 = QR_MAT(v, mi, 3);
             const float m_c_rfl = QR_MAT(v, mi, 2).w;
             const float m_c_trn = m3.x, m_c_rfr = m3.y, m_rfr_2 = m3.z, m_c_rcp = m3.w;
 
             bool push = false;
-            int  push_stage = 0, push_head = QR_NIL, push_flg = 0;
+            int  push_stage = 0, push_flg = 0;
+            uint32_t push_head = 0;
             float nwx = 0.0f, nwy = 0.0f, nwz = 0.0f;
 
             if (resume == 0)
@@ -1283,7 +1341,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     {
                         push = true;
                         push_stage = 0;
-                        push_head = (int)qr_f2u(side ? s1.x : s1.y);    /* FETCH_IPTR */
+                        push_head = qr_f2u(side ? s1.x : s1.y);         /* FETCH_IPTR */
                         push_flg = l_flg | QR_FLAG_PASS_THRU;
                         cnt.refract++;
                     }
@@ -1363,7 +1421,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 {
                     push = true;
                     push_stage = 1;
-                    push_head = (int)qr_f2u(side ? s1.y : s1.x);        /* FETCH_XPTR */
+                    push_head = qr_f2u(side ? s1.y : s1.x);             /* FETCH_XPTR */
                     push_flg = l_flg | QR_FLAG_PASS_BACK;
                     cnt.reflect++;
                 }
@@ -1382,14 +1440,14 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 f.nrm[0] = nx; f.nrm[1] = ny; f.nrm[2] = nz;
                 f.loc[0] = lcx; f.loc[1] = lcy; f.loc[2] = lcz;
                 f.c_trn = c_trn; f.c_rfl = c_rfl;
-                f.si = cur_si; f.flg = l_flg; f.stage = push_stage;
+                f.so = cur_so; f.flg = l_flg; f.stage = push_stage;
                 ox = hx; oy = hy; oz = hz;
                 rx = nwx; ry = nwy; rz = nwz;
                 t_min = 0.0f;
                 t_max = h.cam_t_max;
                 head = push_head;
                 mode = QR_MODE_CLOSEST;
-                p_obj = cur_si;
+                p_obj = cur_so;
                 p_flg = push_flg;
                 lvl++;
                 walk_again = true;

@@ -26,6 +26,7 @@
 #include <string.h>
 #include <utility>
 #include <vector>
+#include <unordered_map>
 #include "qr_scene_blob.h"
 
 #define QR_KSCENE_FLAG   0x4B534331u    /* "1CSK" */
@@ -42,38 +43,56 @@ struct alignas(16) qr_f4 { float x, y, z, w; };
 #endif
 
 /*
- * List element of the image ("compiled" rt_ELEM).  The reference tracks, while
- * it walks a surface list, whether a transform node is open (ctx_LOCAL(OBJ),
- * tracer.cpp:1377-1421, 1492-1496, 4047-4053); that state only depends on the
- * list, not on the ray, so it is resolved here, once per upload:
- *   surface lists  simd = surface, aux = element to continue at when the
- *                  bounding volume is missed (next of the array's last leaf),
- *                  op  = QR_OP_BV | QR_OP_CACHED
- *   light lists    simd = light, aux = head of the light's shadow list
- *   clip lists     simd = clipper surface or QR_NIL (accum marker),
- *                  aux = trnode's last element (array clippers), op = clip
- *                  side / accum marker (rt_ELEM.data, +-1)
+ * List element of the image ("compiled" rt_ELEM), 8 bytes.  Lists are laid
+ * out SEQUENTIALLY: the successor of element i is element i + 1, a list ends
+ * with an END element, element 0 of the array is an END (the NULL list) and a
+ * tail shared with a list emitted earlier is entered through a JUMP.  So the
+ * walker can load element i + 1 before it has looked at element i.
+ *
+ * The reference tracks, while it walks a surface list, whether a transform
+ * node is open (ctx_LOCAL(OBJ), tracer.cpp:1377-1421, 1492-1496, 4047-4053);
+ * that state only depends on the list, not on the ray, so it is resolved
+ * here, once per upload, into the element's kind / flag bits:
+ *   surface lists  w = surface << 7 | flags | kind,  aux = element to continue
+ *                  at when a bounding volume is missed (successor of the
+ *                  array's last leaf) or the JUMP target
+ *   light lists    w = light, aux = head of the light's shadow list
+ *   clip lists     w = clipper surface << 7 | QR_KC_* bits,
+ *                  aux = trnode's last element (array clippers)
  */
 #if defined(__CUDACC__)
-struct __align__(16) qr_kelem { int32_t simd, next, aux, op; };
+struct __align__(8) qr_kelem { uint32_t w; int32_t aux; };
 #else
-struct alignas(16) qr_kelem { int32_t simd, next, aux, op; };
+struct alignas(8) qr_kelem { uint32_t w; int32_t aux; };
 #endif
 
-#define QR_OP_BV        1   /* bounding-volume element of an array (elm.data & 3 == 1) */
-#define QR_OP_CACHED    2   /* child of the open transform node: diff = node diff - pos */
-#define QR_OP_OPEN      4   /* array with a matrix: opens a transform node */
-#define QR_OP_OWNTRM    8   /* surface with its own matrix, outside any open node */
-#define QR_OP_CLOSE    16   /* last element of the open transform node */
-#define QR_OP_SKIPCLOSE 32  /* a missed bounding volume skips past the node's last element */
+#define QR_KEND         0xFFFFFFFFu     /* END element (kind bits = 7) */
+
+#define QR_K_NOP        0   /* array without a matrix / surface without a solver */
+#define QR_K_PLANE      1   /* srf_t[0] == 1 */
+#define QR_K_QUADRIC    2   /* srf_t[0] == 2 */
+#define QR_K_TWOPLANE   3   /* srf_t[0] == 3 */
+#define QR_K_BV         4   /* bounding volume of an array (elm.data & 3 == 1) */
+#define QR_K_OPEN       5   /* array with a matrix: opens a transform node */
+#define QR_K_JUMP       6   /* continue at aux */
+#define QR_K_END        7
+#define QR_K_KIND(w)    ((w) & 7u)
+
+#define QR_KF_CLOSE      8u /* last element of the open transform node */
+#define QR_KF_OWNTRM    16u /* surface with its own matrix, outside any open node */
+#define QR_KF_SKIPCLOSE 32u /* a missed bounding volume skips past the node's last element */
+#define QR_K_SURF_OFF(w) ((w) & ~127u)  /* byte offset of the surface record (128 B each) */
+
+#define QR_KC_NEG        1u /* clip lists: rt_ELEM.data < 0 (inner side / accum enter) */
+#define QR_KC_ACCUM      2u /* clip lists: accum marker (no surface) */
 
 /*
  * ksurf quads (traversal):
  *   q0  pos.x  pos.y  pos.z  desc
  *   q1  sci.x  sci.y  sci.z  sci.w
  *   q2  scj.x  scj.y  scj.z  props (outer | inner << 16)
- *   q3  min.x  min.y  min.z  clip_head
- *   q4  max.x  max.y  max.z  trnode
+ *   q3  min.x  min.y  min.z  clip_head      (min/max: -inf/+inf when switched off)
+ *   q4  max.x  max.y  max.z  trnode (byte offset of its record)
  *   q5  tci.x  tci.y  tci.z  tcj.x
  *   q6  tcj.y  tcj.z  tck.x  tck.y
  *   q7  tck.z  d_eps  t_eps  c_def
@@ -116,154 +135,208 @@ struct alignas(16) qr_kelem { int32_t simd, next, aux, op; };
 #define QR_D_MM_MASK      (63u << 21)
 #define QR_D_HASCLIP_MASK (1u << 27)
 
-/* host-side packer (plain inline functions; never called from device code) */
+/* host-side packer (plain inline code; never called from device code) */
 
 static inline uint32_t qr_k_align16(uint32_t v) { return (v + 15u) & ~15u; }
 
 static inline float qr_k_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-/* bytes of the kscene image of a (validated) blob */
-static inline size_t qr_kscene_size(const void *blob)
-{
-    const qr_blob_header *h = (const qr_blob_header *)blob;
-    uint32_t off = sizeof(qr_blob_header);
-    off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSURF_QUADS * 16);
-    off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSHADE_QUADS * 16);
-    off = qr_k_align16(off + (uint32_t)h->n_mat * QR_KMAT_QUADS * 16);
-    off = qr_k_align16(off + (uint32_t)h->n_lgt * QR_KLGT_QUADS * 16);
-    off = qr_k_align16(off + (uint32_t)h->n_elem * sizeof(qr_elem));
-    off = qr_k_align16(off + (uint32_t)h->n_tiles * sizeof(int32_t));
-    off = qr_k_align16(off + (uint32_t)h->n_texels * sizeof(uint32_t));
-    return off;
-}
-
 /*
- * Build the kscene image of "blob" in "out" (qr_kscene_size bytes, 16-aligned).
- * Returns 0, or -1 when a surface list is not well nested (an element would be
- * reached both inside and outside an open transform node).
+ * Two steps: plan() validates the lists of a (header-checked) blob, compiles
+ * the per-element state and fixes the sequential element order, so bytes() is
+ * exact; write() then builds the image straight into the destination (the
+ * pinned staging buffer of qr_scene_upload).
  */
-static inline int qr_kscene_pack(const void *blob, void *out)
+class qr_kpacker
 {
-    const uint8_t *b = (const uint8_t *)blob;
-    uint8_t *o = (uint8_t *)out;
-    const qr_blob_header *h = (const qr_blob_header *)blob;
-    const qr_surface  *sf = (const qr_surface  *)(b + h->off_surf);
-    const qr_material *mt = (const qr_material *)(b + h->off_mat);
-    const qr_light    *lg = (const qr_light    *)(b + h->off_lgt);
-    const qr_elem     *el = (const qr_elem     *)(b + h->off_elem);
-    const int32_t     *tl = (const int32_t     *)(b + h->off_tiles);
+    public:
 
-    qr_blob_header k = *h;
-    uint32_t off = sizeof(qr_blob_header);
-    k.flags = QR_KSCENE_FLAG;
-    k.off_surf = off;   off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSURF_QUADS * 16);
-    k.pad3[0] = (int32_t)off; off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSHADE_QUADS * 16);
-    k.off_mat = off;    off = qr_k_align16(off + (uint32_t)h->n_mat * QR_KMAT_QUADS * 16);
-    k.off_lgt = off;    off = qr_k_align16(off + (uint32_t)h->n_lgt * QR_KLGT_QUADS * 16);
-    k.off_elem = off;   off = qr_k_align16(off + (uint32_t)h->n_elem * sizeof(qr_elem));
-    k.off_tiles = off;  off = qr_k_align16(off + (uint32_t)h->n_tiles * sizeof(int32_t));
-    k.off_texels = off; off = qr_k_align16(off + (uint32_t)h->n_texels * sizeof(uint32_t));
-    k.total_bytes = off;
-    memcpy(o, &k, sizeof(k));
-
-    qr_f4 *ks = (qr_f4 *)(o + k.off_surf);
-    qr_f4 *kh = (qr_f4 *)(o + (uint32_t)k.pad3[0]);
-    for (int i = 0; i < h->n_surf; i++)
+    /* 0, or -1 when a list is malformed / not well nested (an element would be
+     * reached both inside and outside an open transform node) */
+    int plan(const void *blob_)
     {
-        const qr_surface &s = sf[i];
-        const uint32_t shift = s.a_sgn[3] != 0 ? 1u : 0u;
-        const int sub = shift ? 3 : 0;
-        uint32_t d = 0;
-        d |= ((uint32_t)s.srf_t[0] & 3u);
-        d |= ((uint32_t)s.srf_t[1] & 3u) << 2;
-        d |= ((uint32_t)s.srf_t[2] & 3u) << 4;
-        d |= ((uint32_t)s.conic & 3u) << 6;
-        d |= ((uint32_t)s.a_map[3] & 3u) << 8;
-        d |= shift << 10;
-        d |= (s.srf_t[3] < 0 ? 1u : 0u) << 11;
-        for (int a = 0; a < 3; a++)
+        blob = (const uint8_t *)blob_;
+        h  = (const qr_blob_header *)blob;
+        sf = (const qr_surface  *)(blob + h->off_surf);
+        el = (const qr_elem     *)(blob + h->off_elem);
+        tl = (const int32_t     *)(blob + h->off_tiles);
+        ne = h->n_elem;
+
+        if (compile_surface_lists() != 0) return -1;
+
+        out.clear();
+        nidx.assign((size_t)ne, -1);
+        heads.clear();
+        fix.clear();
+        out.push_back(make(QR_KEND, 0));                /* element 0: the NULL list */
+
+        k_tiles.resize((size_t)h->n_tiles);
+        for (int t = 0; t < h->n_tiles; t++)
         {
-            d |= (s.a_sgn[a] != 0 ? 1u : 0u) << (12 + a);
-            d |= ((uint32_t)(s.a_map[a] - sub) & 3u) << (15 + 2 * a);
+            if ((k_tiles[t] = emit_surf_list(tl[t])) < 0) return -1;
         }
-        d |= ((uint32_t)s.minmax_t & 63u) << 21;
-        d |= (s.clip_head != QR_NIL ? 1u : 0u) << 27;
-
-        const uint32_t props = ((uint32_t)s.props[0] & 0xFFFFu) | (((uint32_t)s.props[1] & 0xFFFFu) << 16);
-        qr_f4 *q = ks + (size_t)i * QR_KSURF_QUADS;
-        q[0].x = s.pos[0]; q[0].y = s.pos[1]; q[0].z = s.pos[2]; q[0].w = qr_k_bits(d);
-        q[1].x = s.sci[0]; q[1].y = s.sci[1]; q[1].z = s.sci[2]; q[1].w = s.sci[3];
-        q[2].x = s.scj[0]; q[2].y = s.scj[1]; q[2].z = s.scj[2]; q[2].w = qr_k_bits(props);
-        q[3].x = s.min[0]; q[3].y = s.min[1]; q[3].z = s.min[2]; q[3].w = qr_k_bits((uint32_t)s.clip_head);
-        q[4].x = s.max[0]; q[4].y = s.max[1]; q[4].z = s.max[2]; q[4].w = qr_k_bits((uint32_t)s.trnode);
-        q[5].x = s.tci[0]; q[5].y = s.tci[1]; q[5].z = s.tci[2]; q[5].w = s.tcj[0];
-        q[6].x = s.tcj[1]; q[6].y = s.tcj[2]; q[6].z = s.tck[0]; q[6].w = s.tck[1];
-        q[7].x = s.tck[2]; q[7].y = s.d_eps;  q[7].z = s.t_eps;  q[7].w = qr_k_bits(s.c_def);
-
-        qr_f4 *g = kh + (size_t)i * QR_KSHADE_QUADS;
-        g[0].x = qr_k_bits((uint32_t)s.mat[0]);     g[0].y = qr_k_bits((uint32_t)s.mat[1]);
-        g[0].z = qr_k_bits((uint32_t)s.lst_lgt[0]); g[0].w = qr_k_bits((uint32_t)s.lst_lgt[1]);
-        g[1].x = qr_k_bits((uint32_t)s.lst_srf[0]); g[1].y = qr_k_bits((uint32_t)s.lst_srf[1]);
-        g[1].z = 0.0f; g[1].w = 0.0f;
-    }
-
-    qr_f4 *km = (qr_f4 *)(o + k.off_mat);
-    for (int i = 0; i < h->n_mat; i++)
-    {
-        const qr_material &m = mt[i];
-        qr_f4 *q = km + (size_t)i * QR_KMAT_QUADS;
-        const uint32_t ys = (m.yshft & 0xFFu) | ((uint32_t)(m.t_map[0] & 1) << 8) | ((uint32_t)(m.t_map[1] & 1) << 9);
-        q[0].x = m.xscal; q[0].y = m.yscal; q[0].z = m.xoffs; q[0].w = m.yoffs;
-        q[1].x = qr_k_bits(m.xmask); q[1].y = qr_k_bits(m.ymask); q[1].z = qr_k_bits(ys); q[1].w = qr_k_bits((uint32_t)m.tex);
-        q[2].x = m.l_dff; q[2].y = m.l_spc; q[2].z = qr_k_bits(m.l_pow); q[2].w = m.c_rfl;
-        q[3].x = m.c_trn; q[3].y = m.c_rfr; q[3].z = m.rfr_2; q[3].w = m.c_rcp;
-        q[4].x = m.ext_2; q[4].y = m.clamp; q[4].z = qr_k_bits(m.cmask); q[4].w = 0.0f;
-    }
-
-    qr_f4 *kl = (qr_f4 *)(o + k.off_lgt);
-    for (int i = 0; i < h->n_lgt; i++)
-    {
-        const qr_light &l = lg[i];
-        qr_f4 *q = kl + (size_t)i * QR_KLGT_QUADS;
-        q[0].x = l.pos[0]; q[0].y = l.pos[1]; q[0].z = l.pos[2]; q[0].w = l.t_max;
-        q[1].x = l.col[0]; q[1].y = l.col[1]; q[1].z = l.col[2]; q[1].w = l.a_qdr;
-        q[2].x = l.a_lnr;  q[2].y = l.a_cnt;  q[2].z = 0.0f;     q[2].w = 0.0f;
-    }
-
-    /* ---- compile the lists ---- */
-    qr_kelem *ke = (qr_kelem *)(o + k.off_elem);
-    const int ne = h->n_elem;
-    for (int i = 0; i < ne; i++)
-    {
-        ke[i].simd = el[i].simd;
-        ke[i].next = el[i].next;
-        ke[i].aux  = el[i].data_p;
-        ke[i].op   = el[i].data_i;      /* light / clip lists keep the raw data */
-    }
-    {
-        /* state[i]: the open trnode's last element when element i of a surface
-         * list is processed (QR_NIL none), -2 = not reached yet */
-        std::vector<int32_t> state((size_t)ne, -2);
-        std::vector<int32_t> roots;
-        for (int t = 0; t < h->n_tiles; t++) roots.push_back(tl[t]);
+        k_srf.assign((size_t)h->n_surf * 2, 0);
+        k_lgt.assign((size_t)h->n_surf * 2, 0);
+        k_clip.assign((size_t)h->n_surf, 0);
         for (int i = 0; i < h->n_surf; i++)
         {
-            roots.push_back(sf[i].lst_srf[0]);
-            roots.push_back(sf[i].lst_srf[1]);
             for (int sd = 0; sd < 2; sd++)
             {
+                if ((k_srf[2 * i + sd] = emit_surf_list(sf[i].lst_srf[sd])) < 0) return -1;
+                if ((k_lgt[2 * i + sd] = emit_copy_list(sf[i].lst_lgt[sd], true)) < 0) return -1;
+            }
+            if ((k_clip[i] = emit_copy_list(sf[i].clip_head, false)) < 0) return -1;
+        }
+        out.push_back(make(QR_KEND, 0));                /* pad: element i + 1 is always loadable */
+
+        /* bounding-volume skip targets: old element -> its sequential index */
+        for (size_t i = 0; i < fix.size(); i++)
+        {
+            const int32_t o = fix[i].second;
+            int32_t n = 0;
+            if (o != QR_NIL)
+            {
+                if (nidx[o] < 0) return -1;
+                n = nidx[o];
+            }
+            out[fix[i].first].aux = n;
+        }
+
+        k = *h;
+        uint32_t off = sizeof(qr_blob_header);
+        k.flags = QR_KSCENE_FLAG;
+        k.off_surf = off;   off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSURF_QUADS * 16);
+        k.pad3[0] = (int32_t)off; off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSHADE_QUADS * 16);
+        k.off_mat = off;    off = qr_k_align16(off + (uint32_t)h->n_mat * QR_KMAT_QUADS * 16);
+        k.off_lgt = off;    off = qr_k_align16(off + (uint32_t)h->n_lgt * QR_KLGT_QUADS * 16);
+        k.off_elem = off;   off = qr_k_align16(off + (uint32_t)out.size() * (uint32_t)sizeof(qr_kelem));
+        k.n_elem = (int32_t)out.size();
+        k.off_tiles = off;  off = qr_k_align16(off + (uint32_t)h->n_tiles * sizeof(int32_t));
+        k.off_texels = off; off = qr_k_align16(off + (uint32_t)h->n_texels * sizeof(uint32_t));
+        k.total_bytes = off;
+        return 0;
+    }
+
+    size_t bytes() const { return k.total_bytes; }
+
+    /* offset of the list elements = size of the part staged in shared memory */
+    uint32_t prefix_bytes() const { return k.off_elem; }
+
+    void write(void *out_) const
+    {
+        uint8_t *o = (uint8_t *)out_;
+        const qr_material *mt = (const qr_material *)(blob + h->off_mat);
+        const qr_light    *lg = (const qr_light    *)(blob + h->off_lgt);
+        const float inf = qr_k_bits(0x7F800000u), ninf = qr_k_bits(0xFF800000u);
+
+        memcpy(o, &k, sizeof(k));
+
+        qr_f4 *ks = (qr_f4 *)(o + k.off_surf);
+        qr_f4 *kh = (qr_f4 *)(o + (uint32_t)k.pad3[0]);
+        for (int i = 0; i < h->n_surf; i++)
+        {
+            const qr_surface &s = sf[i];
+            const uint32_t shift = s.a_sgn[3] != 0 ? 1u : 0u;
+            const int sub = shift ? 3 : 0;
+            uint32_t d = 0;
+            d |= ((uint32_t)s.srf_t[0] & 3u);
+            d |= ((uint32_t)s.srf_t[1] & 3u) << 2;
+            d |= ((uint32_t)s.srf_t[2] & 3u) << 4;
+            d |= ((uint32_t)s.conic & 3u) << 6;
+            d |= ((uint32_t)s.a_map[3] & 3u) << 8;
+            d |= shift << 10;
+            d |= (s.srf_t[3] < 0 ? 1u : 0u) << 11;
+            for (int a = 0; a < 3; a++)
+            {
+                d |= (s.a_sgn[a] != 0 ? 1u : 0u) << (12 + a);
+                d |= ((uint32_t)(s.a_map[a] - sub) & 3u) << (15 + 2 * a);
+            }
+            d |= ((uint32_t)s.minmax_t & 63u) << 21;
+            d |= (s.clip_head != QR_NIL ? 1u : 0u) << 27;
+
+            /* an axis clipper that is switched off can never reject: the
+             * tests are min <= x and !(max < x), tracer.cpp:1874-1927 */
+            const int mm = s.minmax_t;
+            const uint32_t props = ((uint32_t)s.props[0] & 0xFFFFu) | (((uint32_t)s.props[1] & 0xFFFFu) << 16);
+            qr_f4 *q = ks + (size_t)i * QR_KSURF_QUADS;
+            q[0].x = s.pos[0]; q[0].y = s.pos[1]; q[0].z = s.pos[2]; q[0].w = qr_k_bits(d);
+            q[1].x = s.sci[0]; q[1].y = s.sci[1]; q[1].z = s.sci[2]; q[1].w = s.sci[3];
+            q[2].x = s.scj[0]; q[2].y = s.scj[1]; q[2].z = s.scj[2]; q[2].w = qr_k_bits(props);
+            q[3].x = (mm & 1) ? s.min[0] : ninf; q[3].y = (mm & 2) ? s.min[1] : ninf;
+            q[3].z = (mm & 4) ? s.min[2] : ninf; q[3].w = qr_k_bits((uint32_t)k_clip[i]);
+            q[4].x = (mm & 8) ? s.max[0] : inf;  q[4].y = (mm & 16) ? s.max[1] : inf;
+            q[4].z = (mm & 32) ? s.max[2] : inf; q[4].w = qr_k_bits((uint32_t)s.trnode << 7);
+            q[5].x = s.tci[0]; q[5].y = s.tci[1]; q[5].z = s.tci[2]; q[5].w = s.tcj[0];
+            q[6].x = s.tcj[1]; q[6].y = s.tcj[2]; q[6].z = s.tck[0]; q[6].w = s.tck[1];
+            q[7].x = s.tck[2]; q[7].y = s.d_eps;  q[7].z = s.t_eps;  q[7].w = qr_k_bits(s.c_def);
+
+            qr_f4 *g = kh + (size_t)i * QR_KSHADE_QUADS;
+            g[0].x = qr_k_bits((uint32_t)s.mat[0]);         g[0].y = qr_k_bits((uint32_t)s.mat[1]);
+            g[0].z = qr_k_bits((uint32_t)k_lgt[2 * i]);     g[0].w = qr_k_bits((uint32_t)k_lgt[2 * i + 1]);
+            g[1].x = qr_k_bits((uint32_t)k_srf[2 * i]);     g[1].y = qr_k_bits((uint32_t)k_srf[2 * i + 1]);
+            g[1].z = 0.0f; g[1].w = 0.0f;
+        }
+
+        qr_f4 *km = (qr_f4 *)(o + k.off_mat);
+        for (int i = 0; i < h->n_mat; i++)
+        {
+            const qr_material &m = mt[i];
+            qr_f4 *q = km + (size_t)i * QR_KMAT_QUADS;
+            const uint32_t ys = (m.yshft & 0xFFu) | ((uint32_t)(m.t_map[0] & 1) << 8) | ((uint32_t)(m.t_map[1] & 1) << 9);
+            q[0].x = m.xscal; q[0].y = m.yscal; q[0].z = m.xoffs; q[0].w = m.yoffs;
+            q[1].x = qr_k_bits(m.xmask); q[1].y = qr_k_bits(m.ymask); q[1].z = qr_k_bits(ys); q[1].w = qr_k_bits((uint32_t)m.tex);
+            q[2].x = m.l_dff; q[2].y = m.l_spc; q[2].z = qr_k_bits(m.l_pow); q[2].w = m.c_rfl;
+            q[3].x = m.c_trn; q[3].y = m.c_rfr; q[3].z = m.rfr_2; q[3].w = m.c_rcp;
+            q[4].x = m.ext_2; q[4].y = m.clamp; q[4].z = qr_k_bits(m.cmask); q[4].w = 0.0f;
+        }
+
+        qr_f4 *kl = (qr_f4 *)(o + k.off_lgt);
+        for (int i = 0; i < h->n_lgt; i++)
+        {
+            const qr_light &l = lg[i];
+            qr_f4 *q = kl + (size_t)i * QR_KLGT_QUADS;
+            q[0].x = l.pos[0]; q[0].y = l.pos[1]; q[0].z = l.pos[2]; q[0].w = l.t_max;
+            q[1].x = l.col[0]; q[1].y = l.col[1]; q[1].z = l.col[2]; q[1].w = l.a_qdr;
+            q[2].x = l.a_lnr;  q[2].y = l.a_cnt;  q[2].z = 0.0f;     q[2].w = 0.0f;
+        }
+
+        memcpy(o + k.off_elem, out.data(), out.size() * sizeof(qr_kelem));
+        memcpy(o + k.off_tiles, k_tiles.data(), (size_t)h->n_tiles * sizeof(int32_t));
+        memcpy(o + k.off_texels, blob + h->off_texels, (size_t)h->n_texels * sizeof(uint32_t));
+    }
+
+    private:
+
+    static qr_kelem make(uint32_t w, int32_t aux) { qr_kelem e; e.w = w; e.aux = aux; return e; }
+
+    /*
+     * Per old surface-list element: kind / flag bits and the old index of the
+     * bounding-volume skip target.  state[i] is the open trnode's last element
+     * when element i is processed (QR_NIL none), -2 = not reached.
+     */
+    int compile_surface_lists()
+    {
+        flags.assign((size_t)ne, 0);
+        skip.assign((size_t)ne, QR_NIL);
+        std::vector<int32_t> state((size_t)ne, -2);
+        std::vector<std::pair<int32_t, int32_t> > work;     /* (element, state) still to expand */
+
+        for (int t = 0; t < h->n_tiles; t++)
+        {
+            if (tl[t] != QR_NIL) work.push_back(std::make_pair(tl[t], (int32_t)QR_NIL));
+        }
+        for (int i = 0; i < h->n_surf; i++)
+        {
+            for (int sd = 0; sd < 2; sd++)
+            {
+                if (sf[i].lst_srf[sd] != QR_NIL) work.push_back(std::make_pair(sf[i].lst_srf[sd], (int32_t)QR_NIL));
                 int guard = 0;
-                for (int li = sf[i].lst_lgt[sd]; li != QR_NIL && guard <= ne; li = el[li].next, guard++)
+                for (int li = sf[i].lst_lgt[sd]; li != QR_NIL; li = el[li].next)
                 {
-                    roots.push_back(el[li].data_p);
+                    if (li < 0 || li >= ne || guard++ > ne) return -1;
+                    if (el[li].data_p != QR_NIL) work.push_back(std::make_pair(el[li].data_p, (int32_t)QR_NIL));
                 }
             }
-        }
-        /* (element, state) pairs still to expand */
-        std::vector<std::pair<int32_t, int32_t> > work;
-        for (size_t r = 0; r < roots.size(); r++)
-        {
-            if (roots[r] != QR_NIL) work.push_back(std::make_pair(roots[r], (int32_t)QR_NIL));
         }
         while (!work.empty())
         {
@@ -282,21 +355,21 @@ static inline int qr_kscene_pack(const void *blob, void *out)
                 if (e.simd < 0 || e.simd >= h->n_surf) return -1;
                 const qr_surface &s = sf[e.simd];
                 const bool is_array = s.srf_t[3] < 0;
-                int32_t op = 0;
+                uint32_t f = is_array ? (uint32_t)QR_K_NOP : ((uint32_t)s.srf_t[0] & 3u);
                 if (!is_array && lobj != QR_NIL)
                 {
                     if (s.a_sgn[3] == 0) return -1;     /* child without the field shift */
-                    op |= QR_OP_CACHED;
                     if (i == lobj)
                     {
-                        op |= QR_OP_CLOSE;
+                        f |= QR_KF_CLOSE;
                         lobj = QR_NIL;
                     }
                 }
                 else
                 if (is_array && s.a_map[3] != 0)
                 {
-                    op |= QR_OP_OPEN;
+                    if (e.data_i == 1) return -1;       /* a bounding volume has no matrix of its own */
+                    f = QR_K_OPEN;
                     lobj = e.data_p;                    /* tracer.cpp:1492-1496 */
                 }
                 else
@@ -307,27 +380,127 @@ static inline int qr_kscene_pack(const void *blob, void *out)
                 else
                 if (!is_array && s.a_map[3] != 0)
                 {
-                    op |= QR_OP_OWNTRM;
+                    f |= QR_KF_OWNTRM;
                 }
-                int32_t aux = QR_NIL;
                 if (e.data_i == 1)
                 {
-                    op |= QR_OP_BV;
-                    if (e.data_p == lobj) op |= QR_OP_SKIPCLOSE;
+                    f = (f & ~7u) | QR_K_BV;
+                    if (e.data_p == lobj) f |= QR_KF_SKIPCLOSE;
                     if (e.data_p < 0 || e.data_p >= ne) return -1;
-                    aux = el[e.data_p].next;            /* tracer.cpp:4042-4054 */
+                    skip[i] = el[e.data_p].next;        /* tracer.cpp:4042-4054 */
                     const int32_t after = e.data_p == lobj ? (int32_t)QR_NIL : lobj;
-                    if (aux != QR_NIL) work.push_back(std::make_pair(aux, after));
+                    if (skip[i] != QR_NIL) work.push_back(std::make_pair(skip[i], after));
                 }
-                ke[i].op = op;
-                ke[i].aux = aux;
+                flags[i] = f;
                 i = e.next;
             }
         }
+        return 0;
     }
-    memcpy(o + k.off_tiles,  b + h->off_tiles,  (size_t)h->n_tiles * sizeof(int32_t));
-    memcpy(o + k.off_texels, b + h->off_texels, (size_t)h->n_texels * sizeof(uint32_t));
-    return 0;
-}
+
+    /* surface list: emitted once, shared tails entered through a JUMP */
+    int32_t emit_surf_list(int32_t head)
+    {
+        if (head == QR_NIL) return 0;
+        if (head < 0 || head >= ne) return -1;
+        if (nidx[head] >= 0) return nidx[head];
+        const int32_t first = (int32_t)out.size();
+        for (int32_t i = head; ; i = el[i].next)
+        {
+            if (i == QR_NIL)
+            {
+                out.push_back(make(QR_KEND, 0));
+                break;
+            }
+            if (i < 0 || i >= ne) return -1;
+            if (nidx[i] >= 0)
+            {
+                out.push_back(make(QR_K_JUMP, nidx[i]));
+                break;
+            }
+            nidx[i] = (int32_t)out.size();
+            out.push_back(make(((uint32_t)el[i].simd << 7) | flags[i], 0));
+            if (QR_K_KIND(flags[i]) == QR_K_BV)
+            {
+                fix.push_back(std::make_pair(nidx[i], skip[i]));
+            }
+        }
+        return first;
+    }
+
+    /* light / clip list: one private sequential copy per distinct head */
+    int32_t emit_copy_list(int32_t head, bool lights)
+    {
+        if (head == QR_NIL) return 0;
+        if (head < 0 || head >= ne) return -1;
+        {
+            std::unordered_map<int32_t, int32_t>::const_iterator it = heads.find(head);
+            if (it != heads.end()) return it->second;
+        }
+        /* shadow lists first: their indices go into the copy */
+        std::vector<int32_t> shadow;
+        int guard = 0;
+        if (lights)
+        {
+            for (int32_t i = head; i != QR_NIL; i = el[i].next)
+            {
+                if (i < 0 || i >= ne || guard++ > ne) return -1;
+                const int32_t sh = emit_surf_list(el[i].data_p);
+                if (sh < 0) return -1;
+                shadow.push_back(sh);
+            }
+        }
+        const int32_t first = (int32_t)out.size();
+        size_t n = 0;
+        guard = 0;
+        for (int32_t i = head; i != QR_NIL; i = el[i].next, n++)
+        {
+            if (i < 0 || i >= ne || guard++ > ne) return -1;
+            const qr_elem &e = el[i];
+            if (lights)
+            {
+                if (e.simd < 0 || e.simd >= h->n_lgt) return -1;
+                out.push_back(make((uint32_t)e.simd, shadow[n]));
+                continue;
+            }
+            if (e.simd == QR_NIL)
+            {
+                out.push_back(make(QR_KC_ACCUM | (e.data_i < 0 ? QR_KC_NEG : 0u), 0));
+                continue;
+            }
+            if (e.simd < 0 || e.simd >= h->n_surf) return -1;
+            /* array clipper: data_p = the trnode's last element, further down this list */
+            int32_t last = 0;
+            if (e.data_p != QR_NIL)
+            {
+                int32_t pos = 0, g2 = 0;
+                int32_t j = head;
+                for (; j != QR_NIL && j != e.data_p; j = el[j].next, pos++)
+                {
+                    if (j < 0 || j >= ne || g2++ > ne) return -1;
+                }
+                if (j == QR_NIL) return -1;
+                last = first + pos;
+            }
+            out.push_back(make(((uint32_t)e.simd << 7) | (e.data_i < 0 ? QR_KC_NEG : 0u), last));
+        }
+        out.push_back(make(QR_KEND, 0));
+        heads[head] = first;
+        return first;
+    }
+
+    const uint8_t        *blob;
+    const qr_blob_header *h;
+    const qr_surface     *sf;
+    const qr_elem        *el;
+    const int32_t        *tl;
+    int                   ne;
+    qr_blob_header        k;
+    std::vector<uint32_t> flags;
+    std::vector<int32_t>  skip, nidx, k_tiles, k_srf, k_lgt, k_clip;
+    std::vector<qr_kelem> out;
+    std::vector<std::pair<int32_t, int32_t> > fix;
+    std::unordered_map<int32_t, int32_t> heads;
+};
 
 #endif /* QR_KSCENE_H */

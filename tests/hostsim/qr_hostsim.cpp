@@ -28,10 +28,12 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     if (h->version != QR_BLOB_VERSION || h->total_bytes > bytes) return -2;
 
     /* the product path: blob -> packed kscene image (qr_kscene.h) -> core */
-    const size_t kbytes = qr_kscene_size(blob);
+    qr_kpacker pk;
+    if (pk.plan(blob) != 0) return -4;
+    const size_t kbytes = pk.bytes();
     void *kimg = aligned_alloc(64, (kbytes + 63) & ~(size_t)63);
     if (kimg == NULL) return -3;
-    if (qr_kscene_pack(blob, kimg) != 0) { free(kimg); return -4; }
+    pk.write(kimg);
     qr_view<false> v;
     qr_view_init(v, kimg);
 
@@ -39,6 +41,7 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     static const int lane_px[3][4] = { {0, 1, 2, 3}, {0, 0, 1, 1}, {0, 0, 0, 0} };
     qr_frame stack[QR_STACK_DEPTH + 1];
     qr_counters cnt = {0, 0, 0};
+    qr_hitrec best;
     uint64_t primary = 0;
 
     if (y0 < 0) y0 = 0;
@@ -54,7 +57,7 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
             {
                 const int px = x + lane_px[fsaa][l];
                 float col[3];
-                qr_trace_sample<false>(v, px, y, l, stack, col[0], col[1], col[2], tb[l], cnt);
+                qr_trace_sample<false>(v, px, y, l, stack, &best, col[0], col[1], col[2], tb[l], cnt);
                 primary++;
                 for (int k = 0; k < 3; k++) c[k][l] = qr_clamp1(col[k]);
             }
