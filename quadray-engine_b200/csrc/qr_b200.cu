@@ -36,9 +36,10 @@
  * small ones.  QR_B200_SHAPE=<index> overrides the default (tuning only).
  */
 struct qr_shape { int threads, ctas; };
-static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {384, 1}, {128, 4} };
-#define QR_N_SHAPES     6
-#define QR_DEFAULT_SHAPE 0
+static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {384, 1}, {128, 4},
+                                     {896, 1}, {1024, 1} };
+#define QR_N_SHAPES     8
+#define QR_DEFAULT_SHAPE 2
 
 /* ------------------------------------------------------------------ PTX --- */
 
@@ -175,11 +176,11 @@ qr_render_kernel(const qr_launch p)
                     : smp;
 
     qr_frame stack[QR_STACK_DEPTH + 1];
-    /* per-thread best-hit slot behind the staged scene (16 B per thread) */
-    const qr_slot best = smem_u32(qr_smem) + p.stage_bytes + threadIdx.x * 16u;
-    qr_counters cnt;
-    cnt.shadow = cnt.reflect = cnt.refract = 0;
-    unsigned int n_primary = 0;
+    /* per-thread scratch quads behind the staged scene (qr_core.cuh) */
+    qr_scratch sc;
+    sc.addr = smem_u32(qr_smem) + p.stage_bytes + threadIdx.x * 16u;
+    sc.stride = THREADS * 16u;
+    qr_sc_st(sc, QR_SC_MISC, 0.0f, 0.0f, 0.0f, 0.0f);
 
     for (;;)
     {
@@ -202,15 +203,14 @@ qr_render_kernel(const qr_launch p)
             const int px = x0 + lpx;
 
             float col[3] = {0.0f, 0.0f, 0.0f};
-            float t = 0.0f;
             const bool live = px < x_res;
             if (live)
             {
-                qr_trace_sample<STAGED>(v, px, y, lane4, stack, best, col[0], col[1], col[2], t, cnt);
-                n_primary++;
+                qr_trace_sample<STAGED>(v, px, y, lane4, stack, sc, col[0], col[1], col[2]);
                 if (p.t_out != NULL)
                 {
-                    p.t_out[(((size_t)y * x_res + px) << fsaa) + smp] = t;
+                    p.t_out[(((size_t)y * x_res + px) << fsaa) + smp] =
+                        qr_u2f(qr_sc_ld1(sc, QR_SC_MISC, 0));
                 }
             }
             __syncwarp();
@@ -264,17 +264,16 @@ qr_render_kernel(const qr_launch p)
     }
 
     /* ray counters: warp-reduce, one atomic per warp and kind */
-    unsigned int c0 = n_primary, c1 = cnt.shadow, c2 = cnt.reflect, c3 = cnt.refract;
+    unsigned int c1 = qr_sc_ld1(sc, QR_SC_MISC, 1), c2 = qr_sc_ld1(sc, QR_SC_MISC, 2),
+                 c3 = qr_sc_ld1(sc, QR_SC_MISC, 3);
     for (int d = 16; d > 0; d >>= 1)
     {
-        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, d);
         c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, d);
         c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, d);
         c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, d);
     }
     if (lane == 0)
     {
-        atomicAdd(&p.rays[0], (unsigned long long)c0);
         atomicAdd(&p.rays[1], (unsigned long long)c1);
         atomicAdd(&p.rays[2], (unsigned long long)c2);
         atomicAdd(&p.rays[3], (unsigned long long)c3);
@@ -315,6 +314,8 @@ static qr_kernel_fn qr_kernel_of(bool staged, int shape)
         case 3:  return staged ? qr_render_kernel<true, 768, 1> : qr_render_kernel<false, 768, 1>;
         case 4:  return staged ? qr_render_kernel<true, 384, 1> : qr_render_kernel<false, 384, 1>;
         case 5:  return staged ? qr_render_kernel<true, 128, 4> : qr_render_kernel<false, 128, 4>;
+        case 6:  return staged ? qr_render_kernel<true, 896, 1> : qr_render_kernel<false, 896, 1>;
+        case 7:  return staged ? qr_render_kernel<true, 1024, 1> : qr_render_kernel<false, 1024, 1>;
         default: return staged ? qr_render_kernel<true, 256, 2> : qr_render_kernel<false, 256, 2>;
     }
 }
@@ -630,7 +631,7 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
 
     /* shared-memory staging of the kscene prefix */
     const uint32_t prefix = kh->off_elem;
-    const int slots = g_shapes[ctx->shape].threads * 16;       /* per-thread best-hit records */
+    const int slots = g_shapes[ctx->shape].threads * QR_SC_QUADS * 16;     /* per-thread scratch quads */
     const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024 - slots;
     if ((prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
     {
@@ -695,11 +696,17 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     void *args[] = { (void *)&p };
     QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
                                   dim3(grid), dim3(threads), args,
-                                  ctx->stage_bytes + (size_t)threads * 16u, d.stream));
+                                  ctx->stage_bytes + (size_t)threads * QR_SC_QUADS * 16u, d.stream));
     QR_CUDA(ctx, cudaGetLastError());
     QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
     d.timed = true;
     ctx->launches++;
+    {
+        /* primary samples of the band: known without asking the device */
+        int ya = ty0 * ctx->hdr.tile_h, yb = ty1 * ctx->hdr.tile_h;
+        if (yb > ctx->hdr.y_res) yb = ctx->hdr.y_res;
+        if (yb > ya) ctx->rays[0] += ((uint64_t)(yb - ya) * (uint64_t)ctx->hdr.x_res) << ctx->hdr.fsaa;
+    }
     return QR_OK;
 }
 
@@ -1001,7 +1008,7 @@ extern "C" int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info)
     info->regs_per_thread = ctx->fattr.numRegs;
     info->local_bytes_per_thread = (int)ctx->fattr.localSizeBytes;
     info->smem_static_bytes = (int)ctx->fattr.sharedSizeBytes;
-    info->smem_dynamic_bytes = (int)ctx->stage_bytes + g_shapes[ctx->shape].threads * 16;
+    info->smem_dynamic_bytes = (int)ctx->stage_bytes + g_shapes[ctx->shape].threads * QR_SC_QUADS * 16;
     info->scene_in_smem = ctx->stage_bytes != 0;
     return QR_OK;
 }

@@ -147,36 +147,82 @@ template <> struct qr_hot<true>
 #endif
 
 /*
- * Per-thread scratch record for the best hit of a list walk (surface | side,
- * local hit point).  The walk only WRITES it when a nearer candidate passes
- * clipping and the shader reads it once afterwards, so on the device it
- * lives in shared memory (one 16-byte slot per thread, one STS.128 / LDS.128)
- * instead of five registers that every loop iteration would carry along.
+ * Per-thread scratch: a few 16-byte quads in shared memory (device) that take
+ * values which must survive a list walk but are not needed inside it, so they
+ * do not occupy registers in the hot loop:
+ *   BEST  best hit of the walk (surface | side, local hit point): written by
+ *         the walk when a nearer candidate passes clipping, read once by the
+ *         shader afterwards
+ *   LOC   stored local hit of the level the ray starts from (NRM_I/J/K of the
+ *         previous context, tracer.cpp:1352-1373): read by the walk only when
+ *         it meets the surface the ray left
+ *   COL RAY NRM TEX   shading state of a level while its shadow ray is walked
+ *   MISC  primary T_BUF and the ray counters (shadow, reflection, refraction)
+ * Quad q of thread t sits at base + q * stride + t * 16: a warp's 128-bit
+ * access covers 512 contiguous bytes (no bank conflicts).
  */
-struct qr_hitrec { uint32_t so_side; float lx, ly, lz; };
+#define QR_SC_BEST   0
+#define QR_SC_LOC    1
+#define QR_SC_COL    2
+#define QR_SC_RAY    3
+#define QR_SC_NRM    4
+#define QR_SC_TEX    5
+#define QR_SC_MISC   6
+#define QR_SC_QUADS  7
 
+#if defined(__CUDACC__)
+/* (the host pass of nvcc parses these too; it never calls them) */
+struct qr_scratch { uint32_t addr, stride; };   /* shared-window address of quad 0, bytes between quads */
+QR_HD void qr_sc_st(const qr_scratch s, uint32_t q, float a, float b, float c, float d)
+{
 #if defined(__CUDA_ARCH__)
-typedef uint32_t qr_slot;               /* shared-window address of the slot */
-__device__ __forceinline__ void qr_slot_put(qr_slot s, uint32_t so_side, float lx, float ly, float lz)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(s), "r"(so_side), "f"(lx), "f"(ly), "f"(lz) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(s.addr + q * s.stride), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#endif
 }
-__device__ __forceinline__ qr_hitrec qr_slot_get(qr_slot s)
+QR_HD qr_f4 qr_sc_ld(const qr_scratch s, uint32_t q)
 {
-    qr_hitrec r;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.so_side), "=f"(r.lx), "=f"(r.ly), "=f"(r.lz) : "r"(s) : "memory");
+    qr_f4 r = {0.0f, 0.0f, 0.0f, 0.0f};
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(s.addr + q * s.stride) : "memory");
+#endif
     return r;
 }
-#else
-typedef qr_hitrec *qr_slot;
-QR_HD void qr_slot_put(qr_slot s, uint32_t so_side, float lx, float ly, float lz)
+QR_HD void qr_sc_st1(const qr_scratch s, uint32_t q, uint32_t w, uint32_t val)
 {
-    s->so_side = so_side; s->lx = lx; s->ly = ly; s->lz = lz;
-}
-QR_HD qr_hitrec qr_slot_get(qr_slot s) { return *s; }
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.shared.b32 [%0], %1;" :: "r"(s.addr + q * s.stride + w * 4u), "r"(val) : "memory");
 #endif
+}
+QR_HD uint32_t qr_sc_ld1(const qr_scratch s, uint32_t q, uint32_t w)
+{
+    uint32_t val = 0;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val) : "r"(s.addr + q * s.stride + w * 4u) : "memory");
+#endif
+    return val;
+}
+#else
+struct qr_scratch { qr_f4 *quads; };
+QR_HD void qr_sc_st(const qr_scratch s, uint32_t q, float a, float b, float c, float d)
+{
+    s.quads[q].x = a; s.quads[q].y = b; s.quads[q].z = c; s.quads[q].w = d;
+}
+QR_HD qr_f4 qr_sc_ld(const qr_scratch s, uint32_t q) { return s.quads[q]; }
+QR_HD void qr_sc_st1(const qr_scratch s, uint32_t q, uint32_t w, uint32_t val)
+{
+    memcpy((float *)&s.quads[q] + w, &val, 4);
+}
+QR_HD uint32_t qr_sc_ld1(const qr_scratch s, uint32_t q, uint32_t w)
+{
+    uint32_t val; memcpy(&val, (const float *)&s.quads[q] + w, 4); return val;
+}
+#endif
+QR_HD void qr_sc_inc(const qr_scratch s, uint32_t q, uint32_t w)
+{
+    qr_sc_st1(s, q, w, qr_sc_ld1(s, q, w) + 1u);
+}
 
 template <bool SH>
 struct qr_view
@@ -215,12 +261,6 @@ QR_HD void qr_view_init(qr_view<false> &v, const void *img)
     v.tiles  = (const int32_t *)(b + h->off_tiles);
     v.texels = (const uint32_t *)(b + h->off_texels);
 }
-
-/* ray counters, SURVEY.md 8(d): one ray = one list walk for one sample */
-struct qr_counters
-{
-    uint32_t shadow, reflect, refract;
-};
 
 /* continuation of a level that waits for a child ray */
 struct qr_frame
@@ -507,11 +547,12 @@ QR_HD uint32_t qr_side_props(uint32_t packed, int side)
 
 /*
  * One list walk, OO_cyc 1341 .. OO_out 5142, for one sample.
- *   mode CLOSEST: returns true when something was hit; t_buf and *best updated
+ *   mode CLOSEST: returns true when something was hit; t_buf and the scratch
+ *                 quad QR_SC_BEST (surface | side, local hit) are updated
  *   mode SHADOW : returns true when the sample is in shadow (first occluder)
- * (plx, ply, plz) is the stored local hit of the originating level (NRM_I/J/K
- * of the previous context), used when the ray starts on the surface tested
- * (p_obj, tracer.cpp:1352-1373).
+ * The scratch quad QR_SC_LOC holds the stored local hit of the originating
+ * level (NRM_I/J/K of the previous context), used when the ray starts on the
+ * surface tested (p_obj, tracer.cpp:1352-1373).
  *
  * (bo, cr) are the ray origin and direction in the CURRENT frame: the world,
  * or the space of the open transform node (transform caching, tracer.cpp:
@@ -525,8 +566,7 @@ template <bool SH>
 QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                    float ox, float oy, float oz, float rx, float ry, float rz,
                    float t_min, float t_max, uint32_t p_obj, int p_flg,
-                   float plx, float ply, float plz,
-                   float &t_buf, qr_slot best)
+                   const qr_scratch sc, float &t_buf)
 {
     float bo0 = ox, bo1 = oy, bo2 = oz;
     float cr0 = rx, cr1 = ry, cr2 = rz;
@@ -647,7 +687,8 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
             {
                 /* 1352-1373: secondary ray leaving this very surface reuses the
                  * stored local hit as its local diff */
-                ld0 = plx; ld1 = ply; ld2 = plz;
+                const qr_f4 pl = qr_sc_ld(sc, QR_SC_LOC);
+                ld0 = pl.x; ld1 = pl.y; ld2 = pl.z;
             }
 
             /* candidate roots, tried in the order (first, first ^ 1) */
@@ -801,7 +842,7 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 }
                 t_buf = t;
                 found = true;
-                qr_slot_put(best, so | (uint32_t)side, lx, ly, lz);
+                qr_sc_st(sc, QR_SC_BEST, qr_u2f(so | (uint32_t)side), lx, ly, lz);
                 break;
             }
         }
@@ -899,16 +940,24 @@ QR_HD float qr_fresnel(float c, float rfr, float x0, float x7)
 
 /*
  * Trace one primary sample.  "stack" needs QR_STACK_DEPTH frames.
- * Returns the sample colour (before clamp / AA / gamma) and the primary T_BUF.
+ * Returns the sample colour (before clamp / AA / gamma); the primary T_BUF is
+ * left in the scratch (QR_SC_MISC.x).
+ *
+ * Register discipline: the only values that live across a list walk are the
+ * ray itself and a few scalars.  The shading state of the level that casts a
+ * shadow ray is parked in the thread's scratch quads for the duration of the
+ * walk and read back afterwards; the state of a level that waits for a child
+ * ray sits in the continuation stack.  That keeps the walk -- where nearly
+ * all time goes -- at a register count that lets more warps be resident.
  */
 template <bool SH>
 QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
-                           qr_frame *stack, qr_slot best, float &out_r, float &out_g, float &out_b,
-                           float &out_t, qr_counters &cnt)
+                           qr_frame *stack, const qr_scratch sc,
+                           float &out_r, float &out_g, float &out_b)
 {
     const qr_blob_header &h = *v.h;
 
-    /* current ray */
+    /* current ray; after a hit is shaded (ox, oy, oz) is the hit point HIT_X/Y/Z */
     float ox, oy, oz, rx, ry, rz;
     float t_min, t_max;
     uint32_t head, p_obj;
@@ -916,16 +965,13 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
     int   lvl = 0;
 
     /* shading state of the current level */
-    float lrx = 0, lry = 0, lrz = 0;    /* RAY of the level (rx.. may hold a shadow ray) */
-    float hx = 0, hy = 0, hz = 0, nx = 0, ny = 0, nz = 0, lcx = 0, lcy = 0, lcz = 0;
-    float tr = 0, tg = 0, tb = 0, cr = 0, cg = 0, cb = 0;
-    float dot = 0.0f, c_trn = 0.0f, c_rfl = 0.0f;
-    float xr = 0, xg = 0, xb = 0;
-    uint32_t cur_so = QR_SO_NIL, li = 0;
-    int   l_flg = 0;
-
-    /* walk results */
-    float t_buf;
+    float lrx, lry, lrz;                /* RAY of the level (rx.. may hold a shadow ray) */
+    float nx, ny, nz, lcx, lcy, lcz;
+    float tr, tg, tb, cr, cg, cb;
+    float dot, c_trn = 0.0f, c_rfl = 0.0f;
+    float xr = 0.0f, xg = 0.0f, xb = 0.0f;
+    uint32_t cur_so, li;
+    int   l_flg;
 
     /* 1287-1322: primary ray; hor_i / ver_i are exact integers */
     {
@@ -947,30 +993,35 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         p_flg = (int)h.ctx_flags;
     }
 
-    float primary_t = t_max;
-    int resume;                     /* 0 none, 1 after refraction, 2 after reflection, -1 return */
-
     for (;;)
     {
         /* ---------------- WALK ---------------- */
-        float plx = lcx, ply = lcy, plz = lcz;
-        if (mode != QR_MODE_SHADOW && lvl > 0)
-        {
-            plx = stack[lvl - 1].loc[0]; ply = stack[lvl - 1].loc[1]; plz = stack[lvl - 1].loc[2];
-        }
+        float t_buf;
         const bool res = qr_walk<SH>(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
-                                 p_obj, p_flg, plx, ply, plz,
-                                 t_buf, best);
-        bool lights_phase = false;
-        resume = 0;
+                                     p_obj, p_flg, sc, t_buf);
+        int resume = 0;                 /* 0 none, 1 after refraction, 2 after reflection, -1 return */
 
         if (mode == QR_MODE_SHADOW)
         {
+            /* back from a shadow ray: the level's state returns from the scratch */
+            {
+                const qr_f4 a = qr_sc_ld(sc, QR_SC_COL), b = qr_sc_ld(sc, QR_SC_RAY);
+                const qr_f4 c = qr_sc_ld(sc, QR_SC_NRM), d = qr_sc_ld(sc, QR_SC_LOC);
+                const qr_f4 e = qr_sc_ld(sc, QR_SC_TEX);
+                cr = a.x; cg = a.y; cb = a.z; dot = a.w;
+                lrx = b.x; lry = b.y; lrz = b.z; li = qr_f2u(b.w);
+                nx = c.x; ny = c.y; nz = c.z;
+                lcx = d.x; lcy = d.y; lcz = d.z;
+                tr = e.x; tg = e.y; tb = e.z;
+                cur_so = p_obj;
+                l_flg = p_flg & ~(QR_FLAG_PASS | QR_FLAG_SHAD);
+            }
+
             /* LT_ret 2833-3151: light contribution unless occluded */
-            const qr_kelem le = v.elems[li];
             if (!res)
             {
-                const qr_f4 l1 = QR_LGT(v, le.w, 1), l2 = QR_LGT(v, le.w, 2);
+                const uint32_t lgt = v.elems[li].w;
+                const qr_f4 l1 = QR_LGT(v, lgt, 1), l2 = QR_LGT(v, lgt, 2);
                 const qr_f4 sh0 = QR_SHADE(v, cur_so, 0);
                 const int mi = (int)qr_f2u((l_flg & 1) ? sh0.y : sh0.x);
                 const qr_f4 m2 = QR_MAT(v, mi, 2);
@@ -1049,36 +1100,38 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 }
             }
             li = li + 1;
-            lights_phase = true;
         }
         else
         {
-            if (lvl == 0) primary_t = t_buf;
+            if (lvl == 0) qr_sc_st1(sc, QR_SC_MISC, 0, qr_f2u(t_buf));
 
             if (!res)
             {
                 /* nothing hit: COL of this level stays 0 */
                 cr = cg = cb = 0.0f;
                 resume = -1;
+                /* (dead values; keeps every path of the state machine defined) */
+                lrx = lry = lrz = nx = ny = nz = lcx = lcy = lcz = tr = tg = tb = 0.0f;
+                cur_so = QR_SO_NIL; l_flg = 0; li = 0;
             }
             else
             {
                 /* ---------------- SHADE ---------------- */
-                const qr_hitrec hr = qr_slot_get(best);
-                cur_so = hr.so_side & ~127u;
+                const qr_f4 hr = qr_sc_ld(sc, QR_SC_BEST);
+                cur_so = qr_f2u(hr.x) & ~127u;
                 const qr_f4 q1 = QR_SURF(v, cur_so, 1), q2 = QR_SURF(v, cur_so, 2);
                 const uint32_t d = qr_f2u(QR_SURF(v, cur_so, 0).w);
-                const int side = (int)(hr.so_side & 1u);
+                const int side = (int)(qr_f2u(hr.x) & 1u);
                 const uint32_t props = (uint32_t)side | qr_side_props(qr_f2u(q2.w), side);   /* FETCH_PROP */
                 l_flg = (int)props;
                 const qr_f4 s0 = QR_SHADE(v, cur_so, 0);
                 const int mi = (int)qr_f2u(side ? s0.y : s0.x);
 
                 lrx = rx; lry = ry; lrz = rz;
-                hx = qr_add(qr_mul(rx, t_buf), ox);
-                hy = qr_add(qr_mul(ry, t_buf), oy);
-                hz = qr_add(qr_mul(rz, t_buf), oz);
-                lcx = hr.lx; lcy = hr.ly; lcz = hr.lz;
+                ox = qr_add(qr_mul(rx, t_buf), ox);
+                oy = qr_add(qr_mul(ry, t_buf), oy);
+                oz = qr_add(qr_mul(rz, t_buf), oz);
+                lcx = hr.y; lcy = hr.z; lcz = hr.w;
 
                 const uint32_t kind = QR_D_TAG(d) == 1 ? 1u : QR_D_KIND(d);
                 float tex_u = 0.0f, tex_v = 0.0f;
@@ -1122,43 +1175,38 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     n2 = qr_mul(x6, x0);
                 }
 
-                if (props & QR_PROP_NORMAL)
+                /* a material without RT_PROP_NORMAL never reads the normal */
+                nx = n0; ny = n1; nz = n2;
+                if ((props & QR_PROP_NORMAL) && (d & QR_D_TRM_MASK))
                 {
-                    if (d & QR_D_TRM_MASK)
+                    /* MT_nrm 2184-2259: transposed matrix of the trnode */
+                    const uint32_t ti = qr_f2u(QR_SURF(v, cur_so, 4).w);
+                    const qr_f4 t5 = QR_SURF(v, ti, 5), t6 = QR_SURF(v, ti, 6);
+                    const float tck_z = QR_SURF(v, ti, 7).x;
+                    const uint32_t ttrm = QR_D_TRM(qr_f2u(QR_SURF(v, ti, 0).w));
+                    float x4 = qr_mul(t5.x, n0);
+                    float x5 = qr_mul(t6.x, n1);
+                    float x6 = qr_mul(tck_z, n2);
+                    bool renorm = true;
+                    if (ttrm != 1)
                     {
-                        /* MT_nrm 2184-2259: transposed matrix of the trnode */
-                        const uint32_t ti = qr_f2u(QR_SURF(v, cur_so, 4).w);
-                        const qr_f4 t5 = QR_SURF(v, ti, 5), t6 = QR_SURF(v, ti, 6);
-                        const float tck_z = QR_SURF(v, ti, 7).x;
-                        const uint32_t ttrm = QR_D_TRM(qr_f2u(QR_SURF(v, ti, 0).w));
-                        float x4 = qr_mul(t5.x, n0);
-                        float x5 = qr_mul(t6.x, n1);
-                        float x6 = qr_mul(tck_z, n2);
-                        bool renorm = true;
-                        if (ttrm != 1)
-                        {
-                            x4 = qr_add(x4, qr_mul(t5.w, n1));
-                            x4 = qr_add(x4, qr_mul(t6.z, n2));
-                            x5 = qr_add(x5, qr_mul(t5.y, n0));
-                            x5 = qr_add(x5, qr_mul(t6.w, n2));
-                            x6 = qr_add(x6, qr_mul(t5.z, n0));
-                            x6 = qr_add(x6, qr_mul(t6.y, n1));
-                            if (ttrm == 2) renorm = false;
-                        }
-                        if (renorm)
-                        {
-                            float x1 = qr_mul(x4, x4);
-                            x1 = qr_add(x1, qr_mul(x5, x5));
-                            x1 = qr_add(x1, qr_mul(x6, x6));
-                            const float x0 = qr_rsq(x1);
-                            x4 = qr_mul(x4, x0); x5 = qr_mul(x5, x0); x6 = qr_mul(x6, x0);
-                        }
-                        nx = x4; ny = x5; nz = x6;
+                        x4 = qr_add(x4, qr_mul(t5.w, n1));
+                        x4 = qr_add(x4, qr_mul(t6.z, n2));
+                        x5 = qr_add(x5, qr_mul(t5.y, n0));
+                        x5 = qr_add(x5, qr_mul(t6.w, n2));
+                        x6 = qr_add(x6, qr_mul(t5.z, n0));
+                        x6 = qr_add(x6, qr_mul(t6.y, n1));
+                        if (ttrm == 2) renorm = false;
                     }
-                    else
+                    if (renorm)
                     {
-                        nx = n0; ny = n1; nz = n2;
+                        float x1 = qr_mul(x4, x4);
+                        x1 = qr_add(x1, qr_mul(x5, x5));
+                        x1 = qr_add(x1, qr_mul(x6, x6));
+                        const float x0 = qr_rsq(x1);
+                        x4 = qr_mul(x4, x0); x5 = qr_mul(x5, x0); x6 = qr_mul(x6, x0);
                     }
+                    nx = x4; ny = x5; nz = x6;
                 }
 
                 /* MT_mat 2286-2327: texel */
@@ -1197,11 +1245,10 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     cb = qr_mul(tb, h.amb[2]);
                     li = qr_f2u(side ? s0.w : s0.z);
                 }
-                lights_phase = true;
             }
         }
 
-        if (lights_phase)
+        if (resume == 0)
         {
             /* LT_cyc 2762-2831: next light that sees the front of the surface */
             bool go_shadow = false;
@@ -1210,16 +1257,20 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 const qr_kelem le = v.elems[li];
                 if (le.w == QR_KEND) break;
                 const qr_f4 l0 = QR_LGT(v, le.w, 0);
-                const float x1 = qr_sub(l0.x, hx);
-                const float x2 = qr_sub(l0.y, hy);
-                const float x3 = qr_sub(l0.z, hz);
+                const float x1 = qr_sub(l0.x, ox);
+                const float x2 = qr_sub(l0.y, oy);
+                const float x3 = qr_sub(l0.z, oz);
                 float dd = qr_mul(x1, nx);
                 dd = qr_add(dd, qr_mul(x2, ny));
                 dd = qr_add(dd, qr_mul(x3, nz));
                 if (0.0f < dd)
                 {
-                    dot = dd;
-                    ox = hx; oy = hy; oz = hz;
+                    /* shadow ray: park the level, (ox, oy, oz) already is the hit */
+                    qr_sc_st(sc, QR_SC_COL, cr, cg, cb, dd);
+                    qr_sc_st(sc, QR_SC_RAY, lrx, lry, lrz, qr_u2f(li));
+                    qr_sc_st(sc, QR_SC_NRM, nx, ny, nz, 0.0f);
+                    qr_sc_st(sc, QR_SC_LOC, lcx, lcy, lcz, 0.0f);
+                    qr_sc_st(sc, QR_SC_TEX, tr, tg, tb, 0.0f);
                     rx = x1; ry = x2; rz = x3;
                     t_min = 0.0f;
                     t_max = l0.w;
@@ -1227,14 +1278,13 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     mode = QR_MODE_SHADOW;
                     p_obj = cur_so;
                     p_flg = l_flg | QR_FLAG_PASS_BACK | QR_FLAG_SHAD;
-                    cnt.shadow++;
+                    qr_sc_inc(sc, QR_SC_MISC, 1);
                     go_shadow = true;
                     break;
                 }
                 li = li + 1;
             }
             if (go_shadow) continue;
-            resume = 0;
         }
 
         /* ------------- TRANSPARENCY / REFLECTION / unwinding ------------- */
@@ -1250,7 +1300,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 const float ccr = cr, ccg = cg, ccb = cb;
                 cr = f.col[0]; cg = f.col[1]; cb = f.col[2];
                 lrx = f.ray[0]; lry = f.ray[1]; lrz = f.ray[2];
-                hx = f.hit[0]; hy = f.hit[1]; hz = f.hit[2];
+                ox = f.hit[0]; oy = f.hit[1]; oz = f.hit[2];
                 nx = f.nrm[0]; ny = f.nrm[1]; nz = f.nrm[2];
                 lcx = f.loc[0]; lcy = f.loc[1]; lcz = f.loc[2];
                 c_trn = f.c_trn; c_rfl = f.c_rfl;
@@ -1343,7 +1393,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                         push_stage = 0;
                         push_head = qr_f2u(side ? s1.x : s1.y);         /* FETCH_IPTR */
                         push_flg = l_flg | QR_FLAG_PASS_THRU;
-                        cnt.refract++;
+                        qr_sc_inc(sc, QR_SC_MISC, 3);
                     }
                 }
                 if (!push) resume = 1;
@@ -1423,7 +1473,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     push_stage = 1;
                     push_head = qr_f2u(side ? s1.y : s1.x);             /* FETCH_XPTR */
                     push_flg = l_flg | QR_FLAG_PASS_BACK;
-                    cnt.reflect++;
+                    qr_sc_inc(sc, QR_SC_MISC, 2);
                 }
                 else
                 {
@@ -1436,12 +1486,13 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 qr_frame &f = stack[lvl];
                 f.col[0] = cr; f.col[1] = cg; f.col[2] = cb;
                 f.ray[0] = lrx; f.ray[1] = lry; f.ray[2] = lrz;
-                f.hit[0] = hx; f.hit[1] = hy; f.hit[2] = hz;
+                f.hit[0] = ox; f.hit[1] = oy; f.hit[2] = oz;
                 f.nrm[0] = nx; f.nrm[1] = ny; f.nrm[2] = nz;
                 f.loc[0] = lcx; f.loc[1] = lcy; f.loc[2] = lcz;
                 f.c_trn = c_trn; f.c_rfl = c_rfl;
                 f.so = cur_so; f.flg = l_flg; f.stage = push_stage;
-                ox = hx; oy = hy; oz = hz;
+                /* the child's walk finds this level's local hit in the scratch */
+                qr_sc_st(sc, QR_SC_LOC, lcx, lcy, lcz, 0.0f);
                 rx = nwx; ry = nwy; rz = nwz;
                 t_min = 0.0f;
                 t_max = h.cam_t_max;
@@ -1467,7 +1518,6 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
     }
 
     out_r = cr; out_g = cg; out_b = cb;
-    out_t = primary_t;
 }
 
 /* ---- epilogue helpers, XX_end 5221-5343 / FRAME_SIMD 988-1006 -------------- */

@@ -40,8 +40,10 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     const int fsaa = h->fsaa, spp = 1 << fsaa;
     static const int lane_px[3][4] = { {0, 1, 2, 3}, {0, 0, 1, 1}, {0, 0, 0, 0} };
     qr_frame stack[QR_STACK_DEPTH + 1];
-    qr_counters cnt = {0, 0, 0};
-    qr_hitrec best;
+    qr_f4 quads[QR_SC_QUADS];
+    memset(quads, 0, sizeof(quads));
+    qr_scratch sc;
+    sc.quads = quads;
     uint64_t primary = 0;
 
     if (y0 < 0) y0 = 0;
@@ -57,7 +59,8 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
             {
                 const int px = x + lane_px[fsaa][l];
                 float col[3];
-                qr_trace_sample<false>(v, px, y, l, stack, &best, col[0], col[1], col[2], tb[l], cnt);
+                qr_trace_sample<false>(v, px, y, l, stack, sc, col[0], col[1], col[2]);
+                tb[l] = quads[QR_SC_MISC].x;
                 primary++;
                 for (int k = 0; k < 3; k++) c[k][l] = qr_clamp1(col[k]);
             }
@@ -92,7 +95,8 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     free(kimg);
     if (rays != NULL)
     {
-        rays[0] = primary; rays[1] = cnt.shadow; rays[2] = cnt.reflect; rays[3] = cnt.refract;
+        rays[0] = primary;
+        for (int k = 1; k < 4; k++) rays[k] = qr_sc_ld1(sc, QR_SC_MISC, (uint32_t)k);
     }
     return 0;
 }
