@@ -180,6 +180,9 @@ qr_render_kernel(const qr_launch p)
     qr_scratch sc;
     sc.addr = smem_u32(qr_smem) + p.stage_bytes + threadIdx.x * 16u;
     sc.stride = THREADS * 16u;
+    /* opaque to the optimiser: one register, instead of the address being
+     * recomputed from the thread index at every use */
+    asm volatile("mov.u32 %0, %0;" : "+r"(sc.addr));
     qr_sc_st(sc, QR_SC_MISC, 0.0f, 0.0f, 0.0f, 0.0f);
 
     for (;;)

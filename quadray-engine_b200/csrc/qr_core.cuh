@@ -584,36 +584,42 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
     {
         const uint32_t w = e.w;
         const uint32_t kind = QR_K_KIND(w);
-        if (kind >= QR_K_JUMP)
-        {
-            if (kind == QR_K_END) break;
-            ei = (uint32_t)e.aux;
-            e = v.elems[ei];
-            continue;
-        }
-
         uint32_t ni = ei + 1;
-        qr_kelem en = v.elems[ni];              /* successor, in flight during this element */
-
-        do
+        qr_kelem en = v.elems[ni];              /* successor, in flight during this element
+                                                   (the array ends with a spare END) */
+        if (kind > QR_K_TWOPLANE)
         {
-            if (kind == QR_K_NOP) break;
-
-            const uint32_t so = QR_K_SURF_OFF(w);
-            const qr_f4 q0 = QR_SURF(v, so, 0);
-            const uint32_t d = qr_f2u(q0.w);
-
+            /* the rare kinds */
+            if (kind == QR_K_END) break;
+            if (kind == QR_K_JUMP)
+            {
+                ni = (uint32_t)e.aux;
+                en = v.elems[ni];
+            }
+            else
             if (kind == QR_K_OPEN)
             {
                 /* array with a matrix: transform origin diff and ray once for
                  * the elements up to the node's last one (1483-1496) */
+                const uint32_t so = QR_K_SURF_OFF(w);
+                const qr_f4 q0 = QR_SURF(v, so, 0);
                 const qr_f4 q5 = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
                 const float tckz = QR_SURF(v, so, 7).x;
-                qr_xform(q5, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                const uint32_t trm = QR_D_TRM(qr_f2u(q0.w));
+                qr_xform(q5, q6, tckz, trm, qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
                          bo0, bo1, bo2);
-                qr_xform(q5, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
-                break;
+                qr_xform(q5, q6, tckz, trm, rx, ry, rz, cr0, cr1, cr2);
             }
+            ei = ni;
+            e = en;
+            continue;
+        }
+
+        do
+        {
+            const uint32_t so = QR_K_SURF_OFF(w);
+            const qr_f4 q0 = QR_SURF(v, so, 0);
+            const uint32_t d = qr_f2u(q0.w);
 
             if (kind == QR_K_BV)
             {

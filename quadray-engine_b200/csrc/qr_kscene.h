@@ -68,12 +68,12 @@ struct alignas(8) qr_kelem { uint32_t w; int32_t aux; };
 
 #define QR_KEND         0xFFFFFFFFu     /* END element (kind bits = 7) */
 
-#define QR_K_NOP        0   /* array without a matrix / surface without a solver */
+#define QR_K_BV         0   /* bounding volume of an array (elm.data & 3 == 1) */
 #define QR_K_PLANE      1   /* srf_t[0] == 1 */
 #define QR_K_QUADRIC    2   /* srf_t[0] == 2 */
 #define QR_K_TWOPLANE   3   /* srf_t[0] == 3 */
-#define QR_K_BV         4   /* bounding volume of an array (elm.data & 3 == 1) */
-#define QR_K_OPEN       5   /* array with a matrix: opens a transform node */
+#define QR_K_OPEN       4   /* array with a matrix: opens a transform node */
+#define QR_K_NOP        5   /* array without a matrix / surface without a solver */
 #define QR_K_JUMP       6   /* continue at aux */
 #define QR_K_END        7
 #define QR_K_KIND(w)    ((w) & 7u)
@@ -355,7 +355,7 @@ class qr_kpacker
                 if (e.simd < 0 || e.simd >= h->n_surf) return -1;
                 const qr_surface &s = sf[e.simd];
                 const bool is_array = s.srf_t[3] < 0;
-                uint32_t f = is_array ? (uint32_t)QR_K_NOP : ((uint32_t)s.srf_t[0] & 3u);
+                uint32_t f = (is_array || (s.srf_t[0] & 3) == 0) ? (uint32_t)QR_K_NOP : ((uint32_t)s.srf_t[0] & 3u);
                 if (!is_array && lobj != QR_NIL)
                 {
                     if (s.a_sgn[3] == 0) return -1;     /* child without the field shift */
