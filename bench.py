@@ -22,9 +22,12 @@ A step = one render0 pass over one frame (8 294 400 primary samples).
 
   --impl reference   times only the reference's CPU implementation.
 
-N > 1 (torchrun, one rank per GPU): tile rows are split into contiguous bands
-(strong scaling of one frame), every rank renders its band, bands are gathered
-on rank 0 over NCCL.
+N > 1 (torchrun, one rank per GPU): strong scaling of one frame.  Tile rows are
+dealt round-robin (rank r renders rows r, r + N, ...); every rank stores its
+pixels straight into rank 0's framebuffer over NVLink (the buffer is shared
+through a CUDA IPC handle, qr_frame_ipc_*), a tiny NCCL all-reduce tells rank 0
+that everybody is done.  --gather nccl renders into a local buffer and gathers
+the rows with one NCCL gather instead.
 """
 import argparse
 import json
@@ -183,6 +186,14 @@ def main_reference(args, rank, world):
 
 # --------------------------------------------------------------- our arm ---
 
+class _DevArray(object):
+    """Raw device pointer -> torch view (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4",
+                                         "data": (int(ptr), False), "version": 2}
+
+
 def main_gpu(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -204,36 +215,82 @@ def main_gpu(args, rank, world, local_rank):
     ctx.sync()
     hd = ctx.header
     h, w, x_row = hd["y_res"], hd["x_res"], max(hd["x_row"], hd["x_res"])
-    y0, y1 = pkg.band_rows(h, hd["tile_h"], rank, world)
-    rows_max = max(pkg.band_rows(h, hd["tile_h"], r, world)[1] - pkg.band_rows(h, hd["tile_h"], r, world)[0]
-                   for r in range(world))
+    tile_h = hd["tile_h"]
+    tls_col = (h + tile_h - 1) // tile_h
+    slots = (tls_col + world - 1) // world              # tile rows per rank, rounded up
 
-    frame_d = torch.zeros((h, x_row), dtype=torch.int32, device=dev)
-    band_d = torch.zeros((rows_max, x_row), dtype=torch.int32, device=dev)
-    gather_d = [torch.zeros((rows_max, x_row), dtype=torch.int32, device=dev) for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     host_frame = torch.zeros((h, x_row), dtype=torch.int32).pin_memory()
     qstream = torch.cuda.ExternalStream(ctx.stream(0), device=dev)
     cur = torch.cuda.current_stream(dev)
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def gather_bands():
-        """bands -> rank 0's frame over NCCL (the one exchange step per frame)."""
-        band_d[: y1 - y0].copy_(frame_d[y0:y1])
-        dist.gather(band_d, gather_list=gather_d, dst=0)
-        if rank == 0:
-            for r in range(1, world):
-                a, b = pkg.band_rows(h, hd["tile_h"], r, world)
-                frame_d[a:b].copy_(gather_d[r][: b - a])
+    # ---- where the pixels go ------------------------------------------------
+    gather = args.gather if world > 1 else "none"
+    frame_d = None                      # rank 0 (or single GPU): the assembled frame, (h, x_row) int32
+    remote_ptr = None
+    if gather == "p2p":
+        # rank 0's library-owned framebuffer, opened by everybody else
+        handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            if rank == 0:
+                handle.copy_(torch.frombuffer(bytearray(ctx.frame_ipc_export()), dtype=torch.uint8))
+        except Exception as exc:
+            sys.stderr.write("rank 0: CUDA IPC export failed (%r)\n" % (exc,))
+            ok.zero_()
+        dist.broadcast(handle, src=0)
+        try:
+            if rank == 0:
+                frame_ptr, _ = ctx.frame_device()
+            else:
+                remote_ptr = ctx.frame_ipc_open(handle.cpu().numpy().tobytes())
+                frame_ptr = remote_ptr
+        except Exception as exc:                    # IPC not permitted on this box
+            sys.stderr.write("rank %d: CUDA IPC open failed (%r)\n" % (rank, exc))
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if remote_ptr is not None:
+                ctx.frame_ipc_close(remote_ptr)
+                remote_ptr = None
+            gather = "nccl"
+            if rank == 0:
+                sys.stderr.write("bench.py: falling back to the NCCL gather\n")
+        elif rank == 0:
+            frame_d = torch.as_tensor(_DevArray(frame_ptr, (h, x_row)), device=dev)
+    if gather == "nccl":
+        # frame padded to whole slots; tile row t = k * world + r sits at view[k, r]
+        full_d = torch.zeros((slots * world * tile_h, x_row), dtype=torch.int32, device=dev)
+        frame_ptr = full_d.data_ptr()
+        frame_d = full_d[:h]
+        view = full_d.view(slots, world, tile_h, x_row)
+        mine_d = torch.zeros((slots, tile_h, x_row), dtype=torch.int32, device=dev)
+        gather_d = [torch.zeros_like(mine_d) for _ in range(world)] if rank == 0 else None
+    if gather == "none":
+        frame_d = torch.zeros((h, x_row), dtype=torch.int32, device=dev)
+        frame_ptr = frame_d.data_ptr()
+
+    def finish_frame():
+        """After this rank's kernel: make the frame complete on rank 0 (the one
+        exchange step per frame)."""
+        if gather == "p2p":
+            dist.all_reduce(token)                  # everybody's stores have landed
+        elif gather == "nccl":
+            mine_d.copy_(view[:, rank])
+            dist.gather(mine_d, gather_list=gather_d, dst=0)
+            if rank == 0:
+                for r in range(1, world):
+                    view[:, r].copy_(gather_d[r])
 
     def step_device(ev0, ev1):
         flush.fill_(rank + 1)                       # evict L2 between timed iterations
         qstream.wait_stream(cur)
         ev0.record(qstream)
-        ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+        ctx.render_rows(frame_ptr, x_row, rank, world)
         if world > 1:
             cur.wait_stream(qstream)
-            gather_bands()
+            finish_frame()
             ev1.record(cur)
         else:
             ev1.record(qstream)
@@ -276,7 +333,7 @@ def main_gpu(args, rank, world, local_rank):
     rays_measured = float(rays_t.item()) / args.steps
     rays = meta["rays"]["total"]
 
-    # parity of what was just timed (rank 0 holds the gathered frame)
+    # parity of what was just timed (rank 0 holds the assembled frame)
     parity = None
     if rank == 0:
         got = frame_d[:, :w].cpu().numpy().view(np.uint32)
@@ -290,7 +347,7 @@ def main_gpu(args, rank, world, local_rank):
         for _ in range(min(args.steps, 20)):
             flush.fill_(1)
             qstream.wait_stream(cur)
-            ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+            ctx.render_rows(frame_ptr, x_row, 0, 1)
             ctx.sync()
             ks.append(ctx.last_render_ms())
         kern_ms = statistics.mean(ks)
@@ -319,7 +376,7 @@ def main_gpu(args, rank, world, local_rank):
     blob_h = np.ascontiguousarray(blob)
     hf = host_frame.numpy().view(np.uint32)
     h2d = int(blob_h.size)
-    d2h = int(h * x_row * 4) if rank == 0 else 0
+    d2h = int(h * w * 4) if rank == 0 else 0
 
     def step_e2e():
         if world == 1:
@@ -328,9 +385,9 @@ def main_gpu(args, rank, world, local_rank):
         else:
             ctx.upload(blob_h)
             qstream.wait_stream(cur)
-            ctx.render_device(frame_d.data_ptr(), x_row, y0, y1)
+            ctx.render_rows(frame_ptr, x_row, rank, world)
             cur.wait_stream(qstream)
-            gather_bands()
+            finish_frame()
             if rank == 0:
                 host_frame.copy_(frame_d, non_blocking=True)
             torch.cuda.synchronize(dev)
@@ -356,6 +413,10 @@ def main_gpu(args, rank, world, local_rank):
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps
+        sharding = {"none": "single GPU",
+                    "p2p": "tile rows dealt round-robin; every rank stores into rank 0's framebuffer over NVLink "
+                           "(CUDA IPC), one tiny NCCL all-reduce per frame as completion signal",
+                    "nccl": "tile rows dealt round-robin; one NCCL gather to rank 0 per frame"}[gather]
         line = {
             "metric": METRIC, "value": rays * args.steps / (dev_ms * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -367,13 +428,14 @@ def main_gpu(args, rank, world, local_rank):
                        "primary_samples_per_frame": meta["rays"]["primary"],
                        "primary_Msamples_per_s": meta["rays"]["primary"] * args.steps / (dev_ms * 1e-3) / 1e6,
                        "l2": "flushed between timed iterations (256 MB fill)",
-                       "sharding": "contiguous tile-row bands per GPU, gather to rank 0" if world > 1 else "single GPU",
+                       "sharding": sharding,
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
             "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": UNIT,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "qr_scene_upload(host blob) + qr_render(host frame)" if world == 1 else
-                            "qr_scene_upload + qr_render_device band + NCCL gather + D2H on rank 0",
+                    "path": "qr_scene_upload(host blob) + qr_render(pinned host frame; chunked render/D2H pipeline)"
+                            if world == 1 else
+                            "qr_scene_upload + qr_render_rows + frame exchange (%s) + D2H on rank 0" % gather,
                     "pixels_differ_vs_reference_cpu_frame": e2e_parity},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -387,6 +449,10 @@ def main_gpu(args, rank, world, local_rank):
             line["cpu_baseline"] = base
         print(json.dumps(line))
 
+    if remote_ptr is not None:
+        ctx.frame_ipc_close(remote_ptr)
+    if world > 1:
+        dist.barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -400,6 +466,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how the tile rows reach rank 0 (default: P2P stores over NVLink)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -67,28 +67,57 @@ int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes);
 /*
  * Render the uploaded scene: what pfm->render0(s_inf) does for ALL thread
  * indices at once (core/engine/engine.cpp:3284-3298, 3627).  Tile rows are
- * split into contiguous bands across the GPUs of the context, bands are
- * gathered into GPU 0's framebuffer over NVLink (peer copies).
+ * dealt round-robin to the GPUs of the context; peers store their pixels
+ * straight into GPU 0's framebuffer over NVLink (P2P stores from the kernel,
+ * peer copies when P2P is unavailable).
  *   frame  != NULL: host framebuffer of y_res rows, "stride" pixels apart
  *                   (0x00RRGGBB, rt_Scene::get_frame(), engine.cpp:3774-3777);
- *                   the call returns when it holds the finished frame.
+ *                   the call returns when it holds the finished frame.  On
+ *                   one GPU the frame is rendered in a few chunks of tile
+ *                   rows whose D2H overlaps the next chunk's rendering; a
+ *                   page-locked frame receives the D2H directly.
  *   frame  == NULL: render only (asynchronous; see qr_sync / qr_frame_device).
  */
 int qr_render(qr_ctx *ctx, uint32_t *frame, int stride);
 
 /*
  * Render rows [y0, y1) (y0 a multiple of tile_h) into a caller-owned DEVICE
- * buffer that lives on GPU 0 of the context, asynchronously on the context's
- * stream.  Used when the consumer is on the GPU and by one-process-per-GPU
- * drivers that shard tile rows across ranks themselves.
+ * buffer of full-frame geometry that GPU 0 of the context can address,
+ * asynchronously on the context's stream.  Used when the consumer is on the
+ * GPU.
  */
 int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y1);
+
+/*
+ * Render the tile rows tile_row0, tile_row0 + tile_row_step, ... (tile row r
+ * covers frame rows [r * tile_h, (r + 1) * tile_h)) into a DEVICE buffer of
+ * full-frame geometry, asynchronously on the context's stream.  This is the
+ * unit of multi-GPU sharding: rank r of N calls it with (r, N) -- the
+ * interleave the reference's worker threads use for scanlines (index,
+ * index + thnum, ...; core/tracer/tracer.cpp:1142-1151, 5383-5394), at tile
+ * row granularity.  frame_dev may be a peer GPU's buffer (qr_frame_ipc_open or
+ * a peer-enabled pointer): the pixels then travel over NVLink as the kernel
+ * stores them and no gather pass is needed.
+ */
+int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, int tile_row_step);
 
 /* Wait for all queued work of the context. */
 int qr_sync(qr_ctx *ctx);
 
-/* GPU 0's framebuffer of the last qr_render (x_row-strided) and its stride. */
+/* GPU 0's framebuffer for the uploaded scene (x_row-strided; allocated on
+ * first use, holds the last qr_render) and its stride. */
 int qr_frame_device(qr_ctx *ctx, const uint32_t **frame_dev, int *stride);
+
+/*
+ * One process per GPU: the rank that owns the framebuffer exports it
+ * (cudaIpcMemHandle_t, 64 bytes), the other ranks open it and pass the
+ * pointer to qr_render_rows, so every rank stores its tile rows straight into
+ * the owner's framebuffer over NVLink.  The owner must not re-upload a scene
+ * of another frame geometry while the handle is open elsewhere.
+ */
+int qr_frame_ipc_export(qr_ctx *ctx, void *handle64);
+int qr_frame_ipc_open(qr_ctx *ctx, const void *handle64, uint32_t **frame_dev);
+int qr_frame_ipc_close(qr_ctx *ctx, uint32_t *frame_dev);
 
 /*
  * "Dump mode": per primary sample hit distance (ctx_T_BUF at XX_end,

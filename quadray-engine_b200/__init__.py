@@ -23,7 +23,8 @@ QR_OK, QR_E_ARG, QR_E_BLOB, QR_E_CUDA, QR_E_NODEV, QR_E_STATE = 0, -1, -2, -3, -
 # every entry point include/quadray_b200.h declares
 SYMBOLS = (
     "qr_init", "qr_shutdown", "qr_last_error", "qr_scene_upload", "qr_render",
-    "qr_render_device", "qr_sync", "qr_frame_device", "qr_dump_hits",
+    "qr_render_device", "qr_render_rows", "qr_sync", "qr_frame_device",
+    "qr_frame_ipc_export", "qr_frame_ipc_open", "qr_frame_ipc_close", "qr_dump_hits",
     "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
     "qr_kernel_query", "qr_fp32_peak",
 )
@@ -67,6 +68,14 @@ def load_library():
     lib.qr_render.restype = ci
     lib.qr_render_device.argtypes = [vp, vp, ci, ci, ci]
     lib.qr_render_device.restype = ci
+    lib.qr_render_rows.argtypes = [vp, vp, ci, ci, ci]
+    lib.qr_render_rows.restype = ci
+    lib.qr_frame_ipc_export.argtypes = [vp, vp]
+    lib.qr_frame_ipc_export.restype = ci
+    lib.qr_frame_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+    lib.qr_frame_ipc_open.restype = ci
+    lib.qr_frame_ipc_close.argtypes = [vp, vp]
+    lib.qr_frame_ipc_close.restype = ci
     lib.qr_sync.argtypes = [vp]
     lib.qr_sync.restype = ci
     lib.qr_frame_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
@@ -165,6 +174,27 @@ class Context(object):
     def render_device(self, dev_ptr, stride, y0, y1):
         self._check(self.lib.qr_render_device(self.h, ctypes.c_void_p(dev_ptr), int(stride), int(y0), int(y1)))
 
+    def render_rows(self, dev_ptr, stride, tile_row0, tile_row_step):
+        """Tile rows tile_row0, tile_row0 + step, ... into a device buffer of
+        full-frame geometry (possibly another GPU's, see frame_ipc_open)."""
+        self._check(self.lib.qr_render_rows(self.h, ctypes.c_void_p(dev_ptr), int(stride),
+                                            int(tile_row0), int(tile_row_step)))
+
+    def frame_ipc_export(self):
+        """64-byte CUDA IPC handle of GPU 0's framebuffer (bytes)."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.qr_frame_ipc_export(self.h, buf))
+        return buf.raw
+
+    def frame_ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        self._check(self.lib.qr_frame_ipc_open(self.h, ctypes.create_string_buffer(bytes(handle), 64),
+                                               ctypes.byref(p)))
+        return p.value
+
+    def frame_ipc_close(self, dev_ptr):
+        self._check(self.lib.qr_frame_ipc_close(self.h, ctypes.c_void_p(dev_ptr)))
+
     def sync(self):
         self._check(self.lib.qr_sync(self.h))
 
@@ -207,11 +237,15 @@ class Context(object):
         return {n: getattr(k, n) for n, _ in KernelInfo._fields_}
 
 
-def band_rows(y_res, tile_h, rank, world):
-    """Tile-row band [y0, y1) of rank "rank" out of "world" (SURVEY.md 8e):
-    contiguous bands of whole tile rows, the same split qr_render uses across
-    the GPUs of one context."""
+def rank_tile_rows(y_res, tile_h, rank, world):
+    """Tile rows of rank "rank" out of "world" (SURVEY.md 8e): rows rank,
+    rank + world, ... -- the round-robin deal qr_render uses across the GPUs
+    of one context and qr_render_rows(rank, world) renders."""
     tls_col = (y_res + tile_h - 1) // tile_h
-    t0 = tls_col * rank // world
-    t1 = tls_col * (rank + 1) // world
-    return t0 * tile_h, min(t1 * tile_h, y_res)
+    return list(range(rank, tls_col, world))
+
+
+def tile_row_span(y_res, tile_h, tile_row):
+    """Frame rows [y0, y1) of one tile row."""
+    y0 = tile_row * tile_h
+    return y0, min(y0 + tile_h, y_res)

@@ -88,7 +88,9 @@ struct qr_launch
     const uint8_t      *blob;       /* scene blob in global memory */
     uint32_t           *frame;      /* framebuffer (this GPU) */
     int                 stride;     /* pixels per framebuffer row */
-    int                 ty0, ty1;   /* band of tile rows [ty0, ty1) */
+    int                 ty0;        /* first tile row of this launch */
+    int                 ty_step;    /* distance between its tile rows (1 = contiguous band) */
+    int                 n_trows;    /* number of tile rows: ty0, ty0 + ty_step, ... */
     uint32_t            stage_bytes;/* blob prefix staged in smem, 0 = none */
     unsigned int       *queue;      /* work-item counter */
     unsigned long long *rays;       /* [4] ray counters */
@@ -166,7 +168,7 @@ qr_render_kernel(const qr_launch p)
     const int tile_w = h.tile_w, tile_h = h.tile_h;
     const int pk_per_row = (tile_w + ppk - 1) / ppk; /* packets per tile row */
     const unsigned int n_items =
-        (unsigned int)(p.ty1 - p.ty0) * (unsigned int)tiles_x * (unsigned int)tile_h;
+        (unsigned int)p.n_trows * (unsigned int)tiles_x * (unsigned int)tile_h;
 
     /* lane -> (pixel within packet, sample, AA pattern slot), engine.cpp:3465-3550 */
     const int lpx   = lane >> fsaa;
@@ -194,7 +196,7 @@ qr_render_kernel(const qr_launch p)
 
         const int row  = (int)(item % (unsigned int)tile_h);
         const int tile = (int)(item / (unsigned int)tile_h);
-        const int ty   = p.ty0 + tile / tiles_x;
+        const int ty   = p.ty0 + (tile / tiles_x) * p.ty_step;
         const int tx   = tile % tiles_x;
         const int y    = ty * tile_h + row;
         if (y >= y_res) continue;
@@ -324,12 +326,15 @@ static qr_kernel_fn qr_kernel_of(bool staged, int shape)
 }
 
 #define QR_MAX_DEV 16
+#define QR_MAX_CHUNKS 8     /* qr_render to a host frame: render / D2H pipeline depth */
 
 struct qr_dev
 {
     int             id;
     cudaStream_t    stream;
+    cudaStream_t    copy;                           /* D2H of finished chunks (GPU 0) */
     cudaEvent_t     ev0, ev1, done;
+    cudaEvent_t     chunk_ev[QR_MAX_CHUNKS], copy_ev[QR_MAX_CHUNKS];
     uint8_t        *blob_d;     size_t blob_cap;
     uint8_t        *blob_h;     size_t blob_hcap;   /* pinned staging (dev 0 only) */
     uint32_t       *frame_d;    size_t frame_cap;   /* bytes */
@@ -340,7 +345,7 @@ struct qr_dev
     int             sm_count;
     int             ctas_per_sm;
     int             smem_optin;
-    int             ty0, ty1;
+    bool            peer_ok;    /* can store straight into GPU 0's framebuffer */
     bool            timed;
 };
 
@@ -354,6 +359,7 @@ struct qr_ctx
     uint64_t        launches;
     uint64_t        rays[4];
     int             shape;          /* index into g_shapes */
+    int             chunks;         /* qr_render(host frame) pipeline depth on one GPU */
     cudaFuncAttributes fattr;
     qr_kpacker      packer;
     char            err[512];
@@ -433,6 +439,7 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         if ((e = cudaSetDevice(d.id)) != cudaSuccess
         ||  (e = cudaGetDeviceProperties(&prop, d.id)) != cudaSuccess
         ||  (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess
+        ||  (e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking)) != cudaSuccess
         ||  (e = cudaEventCreate(&d.ev0)) != cudaSuccess
         ||  (e = cudaEventCreate(&d.ev1)) != cudaSuccess
         ||  (e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming)) != cudaSuccess
@@ -451,6 +458,16 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
             qr_shutdown(ctx);
             return rc;
         }
+        for (int k = 0; k < QR_MAX_CHUNKS; k++)
+        {
+            if ((e = cudaEventCreateWithFlags(&d.chunk_ev[k], cudaEventDisableTiming)) != cudaSuccess
+            ||  (e = cudaEventCreateWithFlags(&d.copy_ev[k], cudaEventDisableTiming)) != cudaSuccess)
+            {
+                int rc = qr_fail(NULL, QR_E_CUDA, "qr_init: device %d event setup failed: %s", d.id, cudaGetErrorString(e));
+                qr_shutdown(ctx);
+                return rc;
+            }
+        }
         d.sm_count = prop.multiProcessorCount;
         d.smem_optin = (int)prop.sharedMemPerBlockOptin;
         d.ctas_per_sm = 1;
@@ -465,14 +482,20 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         {
             cudaSetDevice(ctx->dev[i].id);
             e = cudaDeviceEnablePeerAccess(ctx->dev[0].id, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-            {
-                cudaGetLastError();
-            }
+            ctx->dev[i].peer_ok = (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled);
+            cudaGetLastError();
         }
     }
 
     ctx->shape = QR_DEFAULT_SHAPE;
+    ctx->chunks = 4;
+    {
+        const char *env = getenv("QR_B200_CHUNKS");
+        if (env != NULL && env[0] >= '1' && env[0] <= '0' + QR_MAX_CHUNKS && env[1] == 0)
+        {
+            ctx->chunks = env[0] - '0';
+        }
+    }
     {
         const char *env = getenv("QR_B200_SHAPE");
         if (env != NULL && env[0] >= '0' && env[0] < '0' + QR_N_SHAPES && env[1] == 0)
@@ -505,6 +528,12 @@ extern "C" void qr_shutdown(qr_ctx *ctx)
         qr_dev &d = ctx->dev[i];
         cudaSetDevice(d.id);
         if (d.stream)  { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+        if (d.copy)    { cudaStreamSynchronize(d.copy); cudaStreamDestroy(d.copy); }
+        for (int k = 0; k < QR_MAX_CHUNKS; k++)
+        {
+            if (d.chunk_ev[k]) cudaEventDestroy(d.chunk_ev[k]);
+            if (d.copy_ev[k])  cudaEventDestroy(d.copy_ev[k]);
+        }
         if (d.ev0)     cudaEventDestroy(d.ev0);
         if (d.ev1)     cudaEventDestroy(d.ev1);
         if (d.done)    cudaEventDestroy(d.done);
@@ -664,13 +693,14 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     return QR_OK;
 }
 
-static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
-                          int ty0, int ty1, float *t_out)
+/* tile rows ty0, ty0 + step, ... (n of them) on GPU i into frame_dev */
+static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
+                          int ty0, int step, int n, float *t_out, bool first = true)
 {
     qr_dev &d = ctx->dev[i];
     QR_CUDA(ctx, cudaSetDevice(d.id));
     d.timed = false;
-    if (ty1 <= ty0)
+    if (n <= 0)
     {
         return QR_OK;
     }
@@ -680,13 +710,14 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     p.frame = frame_dev;
     p.stride = stride;
     p.ty0 = ty0;
-    p.ty1 = ty1;
+    p.ty_step = step;
+    p.n_trows = n;
     p.stage_bytes = ctx->stage_bytes;
     p.queue = d.queue_d;
     p.rays = d.rays_d;
     p.t_out = t_out;
 
-    const unsigned int n_items = (unsigned int)(ty1 - ty0) * ctx->hdr.tls_row * ctx->hdr.tile_h;
+    const unsigned int n_items = (unsigned int)n * ctx->hdr.tls_row * ctx->hdr.tile_h;
     unsigned int grid = (unsigned int)(d.sm_count * d.ctas_per_sm);
     const int threads = g_shapes[ctx->shape].threads;
     const unsigned int warps = (unsigned int)threads / 32u;
@@ -695,7 +726,10 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     if (grid < 1) grid = 1;
 
     QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
-    QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    if (first)
+    {
+        QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    }
     void *args[] = { (void *)&p };
     QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
                                   dim3(grid), dim3(threads), args,
@@ -705,10 +739,15 @@ static int qr_launch_band(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     d.timed = true;
     ctx->launches++;
     {
-        /* primary samples of the band: known without asking the device */
-        int ya = ty0 * ctx->hdr.tile_h, yb = ty1 * ctx->hdr.tile_h;
-        if (yb > ctx->hdr.y_res) yb = ctx->hdr.y_res;
-        if (yb > ya) ctx->rays[0] += ((uint64_t)(yb - ya) * (uint64_t)ctx->hdr.x_res) << ctx->hdr.fsaa;
+        /* primary samples of these rows: known without asking the device */
+        uint64_t rows = 0;
+        for (int k = 0; k < n; k++)
+        {
+            int ya = (ty0 + k * step) * ctx->hdr.tile_h, yb = ya + ctx->hdr.tile_h;
+            if (yb > ctx->hdr.y_res) yb = ctx->hdr.y_res;
+            if (yb > ya) rows += (uint64_t)(yb - ya);
+        }
+        ctx->rays[0] += (rows * (uint64_t)ctx->hdr.x_res) << ctx->hdr.fsaa;
     }
     return QR_OK;
 }
@@ -726,6 +765,16 @@ static int qr_collect_rays(qr_ctx *ctx)
         for (int k = 0; k < 4; k++) ctx->rays[k] += r[k];
     }
     return QR_OK;
+}
+
+static int qr_frame_ensure(qr_ctx *ctx)
+{
+    const qr_blob_header &h = ctx->hdr;
+    const int stride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+    const size_t fbytes = (size_t)stride * h.y_res * sizeof(uint32_t);
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    return qr_grow(ctx, (void **)&d0.frame_d, &d0.frame_cap, fbytes, false);
 }
 
 extern "C" int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y1)
@@ -747,9 +796,37 @@ extern "C" int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, in
     const int ty0 = y0 / h.tile_h;
     const int ty1 = (y1 + h.tile_h - 1) / h.tile_h;
     for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
-    return qr_launch_band(ctx, 0, frame_dev, stride, ty0, ty1, NULL);
+    return qr_launch_rows(ctx, 0, frame_dev, stride, ty0, 1, ty1 - ty0, NULL);
 }
 
+extern "C" int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, int tile_row_step)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_rows: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    if (frame_dev == NULL || stride < h.x_res || tile_row0 < 0 || tile_row_step < 1)
+    {
+        return qr_fail(ctx, QR_E_ARG, "qr_render_rows: bad arguments");
+    }
+    const int n = tile_row0 < h.tls_col ? (h.tls_col - tile_row0 + tile_row_step - 1) / tile_row_step : 0;
+    for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
+    return qr_launch_rows(ctx, 0, frame_dev, stride, tile_row0, tile_row_step, n, NULL);
+}
+
+/*
+ * One frame on all GPUs of the context.  Tile rows are dealt round-robin
+ * (GPU i renders rows i, i + ndev, ...: neighbouring rows cost about the same,
+ * so the GPUs finish together).  GPU 0 owns the framebuffer; a peer with P2P
+ * access stores its pixels straight into it over NVLink from the kernel's
+ * epilogue -- the gather costs no extra pass -- otherwise it renders into a
+ * local buffer of the same geometry and the rows are copied over afterwards.
+ */
 static int qr_render_all(qr_ctx *ctx, float *t_out_dev)
 {
     const qr_blob_header &h = ctx->hdr;
@@ -758,47 +835,55 @@ static int qr_render_all(qr_ctx *ctx, float *t_out_dev)
     const int ndev = t_out_dev != NULL ? 1 : ctx->ndev;
     int rc;
 
-    /* GPU 0 owns the full framebuffer; peers render their band into a local
-     * buffer of the same geometry and push it over NVLink */
-    for (int i = 0; i < ndev; i++)
+    rc = qr_frame_ensure(ctx);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    qr_dev &d0 = ctx->dev[0];
+    for (int i = 1; i < ndev; i++)
     {
         qr_dev &d = ctx->dev[i];
-        QR_CUDA(ctx, cudaSetDevice(d.id));
-        rc = qr_grow(ctx, (void **)&d.frame_d, &d.frame_cap, fbytes, false);
-        if (rc != QR_OK)
+        if (!d.peer_ok)
         {
-            return rc;
+            QR_CUDA(ctx, cudaSetDevice(d.id));
+            rc = qr_grow(ctx, (void **)&d.frame_d, &d.frame_cap, fbytes, false);
+            if (rc != QR_OK)
+            {
+                return rc;
+            }
         }
-        d.ty0 = (int)((long long)h.tls_col * i / ndev);
-        d.ty1 = (int)((long long)h.tls_col * (i + 1) / ndev);
     }
     for (int i = ndev; i < ctx->ndev; i++) ctx->dev[i].timed = false;
 
     for (int i = 0; i < ndev; i++)
     {
         qr_dev &d = ctx->dev[i];
-        rc = qr_launch_band(ctx, i, d.frame_d, stride, d.ty0, d.ty1, t_out_dev);
+        const int n = i < h.tls_col ? (h.tls_col - i + ndev - 1) / ndev : 0;
+        uint32_t *dst = (i == 0 || d.peer_ok) ? d0.frame_d : d.frame_d;
+        rc = qr_launch_rows(ctx, i, dst, stride, i, ndev, n, t_out_dev);
         if (rc != QR_OK)
         {
             return rc;
         }
     }
 
-    /* gather: band rows of GPU i -> GPU 0's framebuffer */
-    qr_dev &d0 = ctx->dev[0];
+    /* GPU 0's stream continues when every peer's rows have landed */
     for (int i = 1; i < ndev; i++)
     {
         qr_dev &d = ctx->dev[i];
-        if (d.ty1 <= d.ty0)
-        {
-            continue;
-        }
-        int ya = d.ty0 * h.tile_h, yb = d.ty1 * h.tile_h;
-        if (yb > h.y_res) yb = h.y_res;
-        const size_t off = (size_t)ya * stride;
-        const size_t n = (size_t)(yb - ya) * stride * sizeof(uint32_t);
         QR_CUDA(ctx, cudaSetDevice(d.id));
-        QR_CUDA(ctx, cudaMemcpyPeerAsync(d0.frame_d + off, d0.id, d.frame_d + off, d.id, n, d.stream));
+        if (!d.peer_ok)
+        {
+            for (int ty = i; ty < h.tls_col; ty += ndev)
+            {
+                int ya = ty * h.tile_h, yb = ya + h.tile_h;
+                if (yb > h.y_res) yb = h.y_res;
+                const size_t off = (size_t)ya * stride;
+                const size_t n = (size_t)(yb - ya) * stride * sizeof(uint32_t);
+                QR_CUDA(ctx, cudaMemcpyPeerAsync(d0.frame_d + off, d0.id, d.frame_d + off, d.id, n, d.stream));
+            }
+        }
         QR_CUDA(ctx, cudaEventRecord(d.done, d.stream));
         QR_CUDA(ctx, cudaSetDevice(d0.id));
         QR_CUDA(ctx, cudaStreamWaitEvent(d0.stream, d.done, 0));
@@ -821,35 +906,95 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     {
         return qr_fail(ctx, QR_E_ARG, "qr_render: stride smaller than x_res");
     }
-    int rc = qr_render_all(ctx, NULL);
-    if (rc != QR_OK || frame == NULL)
+    if (frame == NULL)
     {
-        return rc;
+        return qr_render_all(ctx, NULL);
     }
 
-    /* D2H of the finished frame: pinned staging, then rows into the caller's
-     * (possibly bottom-up, negative stride) framebuffer */
     qr_dev &d0 = ctx->dev[0];
     const int dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
     const size_t fbytes = (size_t)dstride * h.y_res * sizeof(uint32_t);
+    int rc;
     QR_CUDA(ctx, cudaSetDevice(d0.id));
-    rc = qr_grow(ctx, (void **)&d0.frame_h, &d0.frame_hcap, fbytes, true);
-    if (rc != QR_OK)
+
+    /* a caller's frame in page-locked memory (XShm segments are not, but a
+     * registered or cudaMallocHost'ed buffer is) takes the D2H directly;
+     * anything else, and bottom-up frames, go through pinned staging */
+    bool direct = false;
+    if (stride > 0)
     {
-        return rc;
-    }
-    QR_CUDA(ctx, cudaMemcpyAsync(d0.frame_h, d0.frame_d, fbytes, cudaMemcpyDeviceToHost, d0.stream));
-    QR_CUDA(ctx, cudaStreamSynchronize(d0.stream));
-    if (stride == dstride && dstride == h.x_res)
-    {
-        memcpy(frame, d0.frame_h, fbytes);
-    }
-    else
-    {
-        for (int y = 0; y < h.y_res; y++)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost)
         {
-            memcpy(frame + (ptrdiff_t)y * stride, d0.frame_h + (size_t)y * dstride,
-                   (size_t)h.x_res * sizeof(uint32_t));
+            direct = true;
+        }
+        cudaGetLastError();
+    }
+    if (!direct)
+    {
+        rc = qr_grow(ctx, (void **)&d0.frame_h, &d0.frame_hcap, fbytes, true);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+    }
+    uint32_t *dst = direct ? frame : d0.frame_h;
+    const size_t dpitch = (size_t)(direct ? stride : dstride) * sizeof(uint32_t);
+    const size_t spitch = (size_t)dstride * sizeof(uint32_t);
+    const size_t wbytes = (size_t)h.x_res * sizeof(uint32_t);
+
+    /* chunks of tile rows: the D2H (and the host copy out of staging) of
+     * chunk k overlaps the rendering of chunk k + 1 */
+    int nch = ctx->ndev == 1 ? ctx->chunks : 1;
+    if (nch > h.tls_col) nch = h.tls_col;
+    if (nch < 1) nch = 1;
+
+    if (ctx->ndev == 1)
+    {
+        rc = qr_frame_ensure(ctx);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+    }
+    for (int k = 0; k < nch; k++)
+    {
+        const int ta = (int)((long long)h.tls_col * k / nch);
+        const int tb = (int)((long long)h.tls_col * (k + 1) / nch);
+        int ya = ta * h.tile_h, yb = tb * h.tile_h;
+        if (yb > h.y_res) yb = h.y_res;
+        if (ctx->ndev == 1)
+        {
+            rc = qr_launch_rows(ctx, 0, d0.frame_d, dstride, ta, 1, tb - ta, NULL, k == 0);
+        }
+        else
+        {
+            rc = qr_render_all(ctx, NULL);
+        }
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+        QR_CUDA(ctx, cudaEventRecord(d0.chunk_ev[k], d0.stream));
+        QR_CUDA(ctx, cudaStreamWaitEvent(d0.copy, d0.chunk_ev[k], 0));
+        QR_CUDA(ctx, cudaMemcpy2DAsync((uint8_t *)dst + (size_t)ya * dpitch, dpitch,
+                                       (const uint8_t *)d0.frame_d + (size_t)ya * spitch, spitch,
+                                       wbytes, (size_t)(yb - ya), cudaMemcpyDeviceToHost, d0.copy));
+        QR_CUDA(ctx, cudaEventRecord(d0.copy_ev[k], d0.copy));
+    }
+    for (int k = 0; k < nch; k++)
+    {
+        QR_CUDA(ctx, cudaEventSynchronize(d0.copy_ev[k]));
+        if (!direct)
+        {
+            const int ta = (int)((long long)h.tls_col * k / nch);
+            const int tb = (int)((long long)h.tls_col * (k + 1) / nch);
+            int ya = ta * h.tile_h, yb = tb * h.tile_h;
+            if (yb > h.y_res) yb = h.y_res;
+            for (int y = ya; y < yb; y++)
+            {
+                memcpy(frame + (ptrdiff_t)y * stride, d0.frame_h + (size_t)y * dstride, wbytes);
+            }
         }
     }
     return QR_OK;
@@ -875,12 +1020,67 @@ extern "C" int qr_frame_device(qr_ctx *ctx, const uint32_t **frame_dev, int *str
     {
         return QR_E_ARG;
     }
-    if (!ctx->have_scene || ctx->dev[0].frame_d == NULL)
+    if (!ctx->have_scene)
     {
-        return qr_fail(ctx, QR_E_STATE, "qr_frame_device: nothing rendered yet");
+        return qr_fail(ctx, QR_E_STATE, "qr_frame_device: no scene uploaded");
+    }
+    int rc = qr_frame_ensure(ctx);
+    if (rc != QR_OK)
+    {
+        return rc;
     }
     *frame_dev = ctx->dev[0].frame_d;
     *stride = ctx->hdr.x_row >= ctx->hdr.x_res ? ctx->hdr.x_row : ctx->hdr.x_res;
+    return QR_OK;
+}
+
+extern "C" int qr_frame_ipc_export(qr_ctx *ctx, void *handle64)
+{
+    if (ctx == NULL || handle64 == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_frame_ipc_export: no scene uploaded");
+    }
+    int rc = qr_frame_ensure(ctx);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    cudaIpcMemHandle_t hnd;
+    QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    QR_CUDA(ctx, cudaIpcGetMemHandle(&hnd, ctx->dev[0].frame_d));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hnd, sizeof(hnd));
+    return QR_OK;
+}
+
+extern "C" int qr_frame_ipc_open(qr_ctx *ctx, const void *handle64, uint32_t **frame_dev)
+{
+    if (ctx == NULL || handle64 == NULL || frame_dev == NULL)
+    {
+        return QR_E_ARG;
+    }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, sizeof(hnd));
+    void *ptr = NULL;
+    QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    QR_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    *frame_dev = (uint32_t *)ptr;
+    return QR_OK;
+}
+
+extern "C" int qr_frame_ipc_close(qr_ctx *ctx, uint32_t *frame_dev)
+{
+    if (ctx == NULL || frame_dev == NULL)
+    {
+        return QR_E_ARG;
+    }
+    QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[0].stream));
+    QR_CUDA(ctx, cudaIpcCloseMemHandle(frame_dev));
     return QR_OK;
 }
 

@@ -101,12 +101,49 @@ def test_gpu_render_device_bands(entry, pkg, ctx):
     ctx.upload(blob)
     buf = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
     torch.cuda.synchronize()
+    tls_col = (h + 7) // 8
     for r in range(3):
-        y0, y1 = pkg.band_rows(h, 8, r, 3)
-        ctx.render_device(buf.data_ptr(), w, y0, y1)
+        t0, t1 = tls_col * r // 3, tls_col * (r + 1) // 3
+        ctx.render_device(buf.data_ptr(), w, t0 * 8, min(t1 * 8, h))
     ctx.sync()
     got = buf.cpu().numpy().view(np.uint32)
     assert np.array_equal(got, ref)
+
+
+def test_gpu_render_rows_interleaved(entry, pkg, ctx):
+    """qr_render_rows(rank, world): tile rows dealt round-robin assemble into
+    the full frame; each call touches only its own rows."""
+    import torch
+    blob, ref, _ = entry.load_golden("test05_odd")
+    h, w = ref.shape
+    ctx.upload(blob)
+    for world in (2, 3, 8):
+        buf = torch.zeros((h, w), dtype=torch.int32, device="cuda:0")
+        torch.cuda.synchronize()
+        ctx.render_rows(buf.data_ptr(), w, 1, world)
+        ctx.sync()
+        part = buf.cpu().numpy().view(np.uint32)
+        mask = np.zeros(h, dtype=bool)
+        for tr in pkg.rank_tile_rows(h, 8, 1, world):
+            y0, y1 = pkg.tile_row_span(h, 8, tr)
+            mask[y0:y1] = True
+        assert np.array_equal(part[mask], ref[mask]) and not part[~mask].any()
+        for r in [x for x in range(world) if x != 1]:
+            ctx.render_rows(buf.data_ptr(), w, r, world)
+        ctx.sync()
+        assert np.array_equal(buf.cpu().numpy().view(np.uint32), ref)
+
+
+def test_gpu_render_into_pinned_frame(entry, ctx):
+    """A page-locked caller frame takes the chunked D2H directly."""
+    import torch
+    blob, ref, _ = entry.load_golden("test14_full_a4")
+    h, w = ref.shape
+    ctx.upload(blob)
+    pinned = torch.full((h, w + 5), -1, dtype=torch.int32).pin_memory()
+    ctx._check(ctx.lib.qr_render(ctx.h, pinned.data_ptr(), w + 5))
+    got = pinned.numpy().view(np.uint32)
+    assert np.array_equal(got[:, :w], ref) and (got[:, w:] == 0xFFFFFFFF).all()
 
 
 def test_gpu_render_is_deterministic(entry, ctx):
@@ -162,8 +199,8 @@ def test_gpu_full_size_properties(entry, ctx):
 
 
 def test_gpu_multi_device_context(entry, pkg):
-    """One context over several GPUs: tile-row bands per GPU, peer gather to
-    GPU 0.  Needs >= 2 visible devices."""
+    """One context over several GPUs: tile rows dealt round-robin, peers store
+    into GPU 0's framebuffer over NVLink.  Needs >= 2 devices."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:

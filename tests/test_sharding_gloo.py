@@ -1,8 +1,9 @@
-"""Multi-GPU path on the CPU: world_size-2 gloo.  Each rank owns a band of
-tile rows (quadray_engine_b200.band_rows, the split qr_render uses across
-GPUs), renders it -- here with the oracle standing in for the device -- and
-rank 0 gathers the bands; the assembled frame must equal the single-rank one.
-This is the host logic of SURVEY.md 8e (tile-row bands + one gather)."""
+"""Multi-GPU path on the CPU: world_size-2 gloo.  Each rank owns the tile rows
+rank, rank + world, ... (quadray_engine_b200.rank_tile_rows, the deal
+qr_render_rows(rank, world) renders and qr_render uses across GPUs), renders
+them -- here with the oracle standing in for the device -- and rank 0 gathers
+them; the assembled frame must equal the single-rank one.  This is the host
+logic of SURVEY.md 8e (tile rows dealt round-robin + one gather)."""
 import os
 import sys
 
@@ -23,31 +24,40 @@ def _worker(rank, world, port, out_path):
     pkg = ge.load_package()
     blob, ref, meta = ge.load_golden("test05_odd")
     h, w = ref.shape
-    y0, y1 = pkg.band_rows(h, 8, rank, world)
-    band, _, _ = ge.oracle_render(blob, packet=1, y0=y0, y1=y1)
-    mine = torch.from_numpy(band[y0:y1].astype(np.int64))
+    tile_h = 8
+    tls_col = (h + tile_h - 1) // tile_h
+    rows_max = (tls_col + world - 1) // world
+    # this rank's tile rows, compacted: slot k holds tile row rank + k * world
+    mine = torch.zeros((rows_max, tile_h, w), dtype=torch.int64)
+    for k, tr in enumerate(pkg.rank_tile_rows(h, tile_h, rank, world)):
+        y0, y1 = pkg.tile_row_span(h, tile_h, tr)
+        part, _, _ = ge.oracle_render(blob, packet=1, y0=y0, y1=y1)
+        mine[k, : y1 - y0] = torch.from_numpy(part[y0:y1].astype(np.int64))
+    bufs = [torch.zeros_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gather_list=bufs, dst=0)
     if rank == 0:
-        frame = torch.zeros((h, w), dtype=torch.int64)
-        frame[y0:y1] = mine
-        for r in range(1, world):
-            a, b = pkg.band_rows(h, 8, r, world)
-            buf = torch.zeros((b - a, w), dtype=torch.int64)
-            dist.recv(buf, src=r)
-            frame[a:b] = buf
-        np.save(out_path, frame.numpy().astype(np.uint32))
-    else:
-        dist.send(mine, dst=0)
+        frame = np.zeros((h, w), dtype=np.uint32)
+        for r in range(world):
+            for k, tr in enumerate(pkg.rank_tile_rows(h, tile_h, r, world)):
+                y0, y1 = pkg.tile_row_span(h, tile_h, tr)
+                frame[y0:y1] = bufs[r][k, : y1 - y0].numpy().astype(np.uint32)
+        np.save(out_path, frame)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_band_rows_cover_the_frame(pkg):
+def test_tile_rows_cover_the_frame(pkg):
     for y_res in (480, 1080, 250, 7, 2160):
         for world in (1, 2, 3, 4, 8):
-            rows = [pkg.band_rows(y_res, 8, r, world) for r in range(world)]
-            assert rows[0][0] == 0 and rows[-1][1] == y_res
-            for (a0, a1), (b0, b1) in zip(rows, rows[1:]):
-                assert a1 == b0 and a0 % 8 == 0 and b0 % 8 == 0
+            tls_col = (y_res + 7) // 8
+            seen = sorted(tr for r in range(world) for tr in pkg.rank_tile_rows(y_res, 8, r, world))
+            assert seen == list(range(tls_col))
+            spans = [pkg.tile_row_span(y_res, 8, tr) for tr in seen]
+            assert spans[0][0] == 0 and spans[-1][1] == y_res
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0
+            sizes = [len(pkg.rank_tile_rows(y_res, 8, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
 
 
 def test_two_ranks_gather_equals_single(tmp_path, entry):
