@@ -81,10 +81,16 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     const char *ps = getenv("QR_ORACLE_PACKET");
     int packet = ps != NULL ? atoi(ps) : 1;
 
+    /* QR_ORACLE_ROWS=n: render only the first n rows (fixture generation
+     * that is after the blob, not the frame) */
+    const char *rs = getenv("QR_ORACLE_ROWS");
+    int rows = rs != NULL ? atoi(rs) : (int)s_inf->frm_h;
+    if (rows < 0 || rows > (int)s_inf->frm_h) rows = (int)s_inf->frm_h;
+
     qr_oracle_stats st;
     int rc = qr_oracle_render(blob, bytes, (uint32_t *)s_inf->frame,
                               (int)s_inf->frm_row, packet, NULL,
-                              0, (int)s_inf->frm_h, &st);
+                              0, rows, &st);
     if (rc != 0)
     {
         throw rt_Exception("qr_oracle_render failed");

@@ -162,10 +162,19 @@ class qr_kpacker
         tl = (const int32_t     *)(blob + h->off_tiles);
         ne = h->n_elem;
 
-        if (compile_surface_lists() != 0) return -1;
+        /* what the list compiler needs of a surface, in one word:
+         * bits 1:0 srf_t[0], 2 array, 3 has a matrix, 4 field shift */
+        sinfo.resize((size_t)h->n_surf);
+        for (int i = 0; i < h->n_surf; i++)
+        {
+            sinfo[i] = (uint8_t)(((uint32_t)sf[i].srf_t[0] & 3u) | (sf[i].srf_t[3] < 0 ? 4u : 0u)
+                               | (sf[i].a_map[3] != 0 ? 8u : 0u) | (sf[i].a_sgn[3] != 0 ? 16u : 0u));
+        }
 
         out.clear();
+        out.reserve((size_t)ne + (size_t)h->n_tiles + 4u * (size_t)h->n_surf + 64u);
         nidx.assign((size_t)ne, -1);
+        state.assign((size_t)ne, QR_NIL);
         heads.clear();
         fix.clear();
         out.push_back(make(QR_KEND, 0));                /* element 0: the NULL list */
@@ -189,17 +198,18 @@ class qr_kpacker
         }
         out.push_back(make(QR_KEND, 0));                /* pad: element i + 1 is always loadable */
 
-        /* bounding-volume skip targets: old element -> its sequential index */
+        /* bounding-volume skip targets: old element -> its sequential index;
+         * the walk arrives there with the node state the skip leaves behind */
         for (size_t i = 0; i < fix.size(); i++)
         {
-            const int32_t o = fix[i].second;
+            const int32_t o = fix[i].target;
             int32_t n = 0;
             if (o != QR_NIL)
             {
-                if (nidx[o] < 0) return -1;
+                if (o < 0 || o >= ne || nidx[o] < 0 || state[o] != fix[i].state) return -1;
                 n = nidx[o];
             }
-            out[fix[i].first].aux = n;
+            out[fix[i].at].aux = n;
         }
 
         k = *h;
@@ -310,120 +320,86 @@ class qr_kpacker
     static qr_kelem make(uint32_t w, int32_t aux) { qr_kelem e; e.w = w; e.aux = aux; return e; }
 
     /*
-     * Per old surface-list element: kind / flag bits and the old index of the
-     * bounding-volume skip target.  state[i] is the open trnode's last element
-     * when element i is processed (QR_NIL none), -2 = not reached.
+     * Surface list: compiled and emitted once; a tail shared with a list
+     * emitted earlier is entered through a JUMP.  "lobj" is the last element
+     * of the open transform node while the list is walked (QR_NIL: none) --
+     * the state the reference keeps in ctx_LOCAL(OBJ); state[i] records it
+     * per element so that every way of reaching an element agrees on it.
      */
-    int compile_surface_lists()
-    {
-        flags.assign((size_t)ne, 0);
-        skip.assign((size_t)ne, QR_NIL);
-        std::vector<int32_t> state((size_t)ne, -2);
-        std::vector<std::pair<int32_t, int32_t> > work;     /* (element, state) still to expand */
-
-        for (int t = 0; t < h->n_tiles; t++)
-        {
-            if (tl[t] != QR_NIL) work.push_back(std::make_pair(tl[t], (int32_t)QR_NIL));
-        }
-        for (int i = 0; i < h->n_surf; i++)
-        {
-            for (int sd = 0; sd < 2; sd++)
-            {
-                if (sf[i].lst_srf[sd] != QR_NIL) work.push_back(std::make_pair(sf[i].lst_srf[sd], (int32_t)QR_NIL));
-                int guard = 0;
-                for (int li = sf[i].lst_lgt[sd]; li != QR_NIL; li = el[li].next)
-                {
-                    if (li < 0 || li >= ne || guard++ > ne) return -1;
-                    if (el[li].data_p != QR_NIL) work.push_back(std::make_pair(el[li].data_p, (int32_t)QR_NIL));
-                }
-            }
-        }
-        while (!work.empty())
-        {
-            int32_t i = work.back().first, lobj = work.back().second;
-            work.pop_back();
-            while (i != QR_NIL)
-            {
-                if (i < 0 || i >= ne) return -1;
-                if (state[i] != -2)
-                {
-                    if (state[i] != lobj) return -1;
-                    break;                              /* suffix already compiled */
-                }
-                state[i] = lobj;
-                const qr_elem &e = el[i];
-                if (e.simd < 0 || e.simd >= h->n_surf) return -1;
-                const qr_surface &s = sf[e.simd];
-                const bool is_array = s.srf_t[3] < 0;
-                uint32_t f = (is_array || (s.srf_t[0] & 3) == 0) ? (uint32_t)QR_K_NOP : ((uint32_t)s.srf_t[0] & 3u);
-                if (!is_array && lobj != QR_NIL)
-                {
-                    if (s.a_sgn[3] == 0) return -1;     /* child without the field shift */
-                    if (i == lobj)
-                    {
-                        f |= QR_KF_CLOSE;
-                        lobj = QR_NIL;
-                    }
-                }
-                else
-                if (is_array && s.a_map[3] != 0)
-                {
-                    if (e.data_i == 1) return -1;       /* a bounding volume has no matrix of its own */
-                    f = QR_K_OPEN;
-                    lobj = e.data_p;                    /* tracer.cpp:1492-1496 */
-                }
-                else
-                if (is_array && lobj != QR_NIL)
-                {
-                    return -1;                          /* plain array inside an open node */
-                }
-                else
-                if (!is_array && s.a_map[3] != 0)
-                {
-                    f |= QR_KF_OWNTRM;
-                }
-                if (e.data_i == 1)
-                {
-                    f = (f & ~7u) | QR_K_BV;
-                    if (e.data_p == lobj) f |= QR_KF_SKIPCLOSE;
-                    if (e.data_p < 0 || e.data_p >= ne) return -1;
-                    skip[i] = el[e.data_p].next;        /* tracer.cpp:4042-4054 */
-                    const int32_t after = e.data_p == lobj ? (int32_t)QR_NIL : lobj;
-                    if (skip[i] != QR_NIL) work.push_back(std::make_pair(skip[i], after));
-                }
-                flags[i] = f;
-                i = e.next;
-            }
-        }
-        return 0;
-    }
-
-    /* surface list: emitted once, shared tails entered through a JUMP */
     int32_t emit_surf_list(int32_t head)
     {
         if (head == QR_NIL) return 0;
         if (head < 0 || head >= ne) return -1;
-        if (nidx[head] >= 0) return nidx[head];
+        if (nidx[head] >= 0) return state[head] == QR_NIL ? nidx[head] : -1;
         const int32_t first = (int32_t)out.size();
-        for (int32_t i = head; ; i = el[i].next)
+        int32_t lobj = QR_NIL;
+        for (int32_t i = head; ; )
         {
             if (i == QR_NIL)
             {
+                if (lobj != QR_NIL) return -1;          /* list ends inside an open node */
                 out.push_back(make(QR_KEND, 0));
                 break;
             }
             if (i < 0 || i >= ne) return -1;
             if (nidx[i] >= 0)
             {
+                if (state[i] != lobj) return -1;
                 out.push_back(make(QR_K_JUMP, nidx[i]));
                 break;
             }
+            const qr_elem &e = el[i];
+            if (e.simd < 0 || e.simd >= h->n_surf) return -1;
+            const uint32_t si = sinfo[e.simd];
+            const bool is_array = (si & 4u) != 0, has_mtx = (si & 8u) != 0;
             nidx[i] = (int32_t)out.size();
-            out.push_back(make(((uint32_t)el[i].simd << 7) | flags[i], 0));
-            if (QR_K_KIND(flags[i]) == QR_K_BV)
+            state[i] = lobj;
+
+            uint32_t f = (is_array || (si & 3u) == 0) ? (uint32_t)QR_K_NOP : (si & 3u);
+            if (!is_array && lobj != QR_NIL)
             {
-                fix.push_back(std::make_pair(nidx[i], skip[i]));
+                if (!(si & 16u)) return -1;             /* child without the field shift */
+                if (i == lobj)
+                {
+                    f |= QR_KF_CLOSE;
+                    lobj = QR_NIL;
+                }
             }
+            else
+            if (is_array && has_mtx)
+            {
+                if (e.data_i == 1) return -1;           /* a bounding volume has no matrix of its own */
+                f = QR_K_OPEN;
+                lobj = e.data_p;                        /* tracer.cpp:1492-1496 */
+            }
+            else
+            if (is_array && lobj != QR_NIL)
+            {
+                return -1;                              /* plain array inside an open node */
+            }
+            else
+            if (!is_array && has_mtx)
+            {
+                f |= QR_KF_OWNTRM;
+            }
+            if (e.data_i == 1)
+            {
+                f = (f & ~7u) | QR_K_BV;
+                if (e.data_p < 0 || e.data_p >= ne) return -1;
+
+                qr_kfix x;
+                x.at = nidx[i];
+                x.target = el[e.data_p].next;           /* tracer.cpp:4042-4054 */
+                x.state = lobj;
+                if (e.data_p == lobj)
+                {
+                    f |= QR_KF_SKIPCLOSE;
+                    x.state = QR_NIL;
+                }
+                fix.push_back(x);
+            }
+            out.push_back(make(((uint32_t)e.simd << 7) | f, 0));
+            i = e.next;
         }
         return first;
     }
@@ -438,7 +414,7 @@ class qr_kpacker
             if (it != heads.end()) return it->second;
         }
         /* shadow lists first: their indices go into the copy */
-        std::vector<int32_t> shadow;
+        shadow.clear();
         int guard = 0;
         if (lights)
         {
@@ -496,10 +472,11 @@ class qr_kpacker
     const int32_t        *tl;
     int                   ne;
     qr_blob_header        k;
-    std::vector<uint32_t> flags;
-    std::vector<int32_t>  skip, nidx, k_tiles, k_srf, k_lgt, k_clip;
+    struct qr_kfix { int32_t at, target, state; };      /* BV element, old skip target, state there */
+    std::vector<uint8_t>  sinfo;
+    std::vector<int32_t>  state, nidx, k_tiles, k_srf, k_lgt, k_clip, shadow;
     std::vector<qr_kelem> out;
-    std::vector<std::pair<int32_t, int32_t> > fix;
+    std::vector<qr_kfix>  fix;
     std::unordered_map<int32_t, int32_t> heads;
 };
 

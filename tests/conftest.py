@@ -13,7 +13,11 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-GOLDEN_ALL = sorted(f[:-4] for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.endswith(".npz"))
+_NPZ = sorted(f[:-4] for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.endswith(".npz"))
+# "...h" fixtures (full-size cases of BASELINE.json configs 3 and 4) hold the
+# reference frame as per-row CRC-32s instead of pixels
+GOLDEN_HASHED = [g for g in _NPZ if g.endswith("h")]
+GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h")]
 # the 1080p frame is the bench workload; CPU tests use the 800x480 cases
 GOLDEN_SMALL = [g for g in GOLDEN_ALL if "1080p" not in g]
 

@@ -7,7 +7,7 @@ distance within 1e-5 relative in dump mode (tolerances written here)."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_ALL, GOLDEN_SMALL
+from conftest import GOLDEN_ALL, GOLDEN_HASHED, GOLDEN_SMALL
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +42,18 @@ def test_gpu_frame_vs_oracle_and_reference(entry, ctx, name):
         return                                      # oracle at 1080p takes ~10 s; reference frame is the check
     want, _, _ = entry.oracle_render(blob, packet=1)
     assert int((got != want).sum()) == 0, meta["args"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_HASHED)
+def test_gpu_full_size_frames_vs_reference(entry, ctx, name):
+    """BASELINE.json configs 3 and 4 at full size (1080p quadric / CSG /
+    Fresnel scenes, 4K demo): every row of the GPU frame has the CRC-32 of the
+    reference's row, i.e. the frames are identical."""
+    blob, rowcrc, meta = entry.load_golden_hashed(name)
+    ctx.upload(blob)
+    got = ctx.render_frame()
+    bad = np.nonzero(entry.row_crcs(got) != rowcrc)[0]
+    assert bad.size == 0, (meta["args"], bad[:10].tolist())
 
 
 def test_gpu_scene_staged_in_shared_memory(entry, ctx):

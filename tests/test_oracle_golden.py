@@ -7,7 +7,7 @@ images, so frames of the reference itself are the known answers.
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_SMALL
+from conftest import GOLDEN_HASHED, GOLDEN_SMALL
 
 # emulating the reference's 32-lane packets must reproduce its frame bit for bit
 PACKET32 = ["test01_full", "test05_full", "test12_full", "test15_full", "test16_full",
@@ -65,3 +65,13 @@ def test_oracle_rejects_bad_blob(entry):
         entry.oracle_render(bad)
     with pytest.raises(RuntimeError):
         entry.oracle_render(blob[:100])
+
+
+@pytest.mark.parametrize("name", GOLDEN_HASHED)
+def test_oracle_rows_of_full_size_fixtures(entry, name):
+    """The full-size fixtures (1080p / 4K, reference frame kept as row CRCs):
+    a few rows through the oracle reproduce the reference's rows exactly."""
+    blob, rowcrc, meta = entry.load_golden_hashed(name)
+    y0 = (meta["y_res"] // 2) & ~7
+    got, _, _ = entry.oracle_render(blob, packet=32, y0=y0, y1=y0 + 4)
+    assert np.array_equal(entry.row_crcs(got[y0:y0 + 4]), rowcrc[y0:y0 + 4]), meta["args"]

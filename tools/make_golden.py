@@ -49,6 +49,45 @@ CASES.update({
 })
 
 
+# Full-size cases (BASELINE.json configs 3 and 4): the reference frame is kept
+# as per-row CRC-32s instead of pixels ("h" suffix) so the fixtures stay small.
+CASES_HASHED = {
+    "test02_1080p_a4h": "-s test02 -p full -x 1920 -y 1080 -a 2",
+    "test09_1080p_h":   "-s test09 -p full -x 1920 -y 1080",
+    "test12_1080p_a4h": "-s test12 -p full -x 1920 -y 1080 -a 2",
+    "test14_1080p_h":   "-s test14 -p full -x 1920 -y 1080",
+    "test15_1080p_a4h": "-s test15 -p full -x 1920 -y 1080 -a 2",
+    "test16_1080p_a4h": "-s test16 -p full -x 1920 -y 1080 -a 2",
+    "test17_1080p_a4h": "-s test17 -p full -x 1920 -y 1080 -a 2",
+    "test18_1080p_a4h": "-s test18 -p full -x 1920 -y 1080 -a 2",
+    "demo03_4k_a4gh":   "-s demo03 -x 3840 -y 2160 -a 2 -g",
+}
+
+
+def row_crcs(frame):
+    import zlib
+    return np.array([zlib.crc32(np.ascontiguousarray(r).tobytes()) for r in frame], dtype=np.uint32)
+
+
+def main_hashed(names):
+    for name in names:
+        args = CASES_HASHED[name].split()
+        with tempfile.TemporaryDirectory() as td:
+            rf, of, bf = (os.path.join(td, n) for n in ("r.raw", "o.raw", "s.blob"))
+            jr = run([REF] + args + ["-o", rf])
+            # the oracle harness only has to flatten: one row is enough
+            run([ORC] + args + ["-o", of], {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_ROWS": "1"})
+            w, h = jr["x_res"], jr["y_res"]
+            frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
+            blob = np.fromfile(bf, dtype=np.uint8)
+        meta = {"name": name, "args": CASES_HASHED[name], "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
+                "opts": jr["opts"], "ref_simd": jr["simd"]}
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, blob=blob, rowcrc=row_crcs(frame),
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print("%-20s %4dx%-4d blob %8d B  npz %7d B" % (name, w, h, blob.size, os.path.getsize(path)))
+
+
 def run(cmd, env=None):
     e = dict(os.environ)
     if env:
@@ -109,4 +148,6 @@ def main(names):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or list(CASES))
+    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED))
+    main([n for n in names if n in CASES])
+    main_hashed([n for n in names if n in CASES_HASHED])

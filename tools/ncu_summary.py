@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""ncu raw page (ncu -i rep --page raw --csv) -> profiles/ncu_summary.json,
+the file bench.py reads the dominant kernel's DRAM traffic from.
+usage: ncu_summary.py raw.csv out.json "<capture command / note>" """
+import csv
+import json
+import sys
+
+raw, out, note = sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ""
+rows = list(csv.reader(open(raw)))
+names, units, vals = rows[0], rows[1], rows[2]
+d = dict(zip(names, zip(vals, units)))
+KEYS = ("gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__inst_executed.avg.per_cycle_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__block_size", "launch__grid_size", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__sass_average_branch_targets_threads_uniform.pct")
+
+
+def to_bytes(v, u):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+
+m = {k: {"value": d[k][0], "unit": d[k][1]} for k in KEYS if k in d}
+res = {"capture": note, "kernel": d.get("Kernel Name", ("", ""))[0], "metrics": m}
+if "dram__bytes_read.sum" in d:
+    res["dram_bytes_per_launch"] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
+json.dump(res, open(out, "w"), indent=1)
+print(json.dumps(res)[:400])
