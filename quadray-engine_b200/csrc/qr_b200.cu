@@ -359,7 +359,9 @@ struct qr_ctx
     uint64_t        launches;
     uint64_t        rays[4];
     int             shape;          /* index into g_shapes */
-    int             chunks;         /* qr_render(host frame) pipeline depth on one GPU */
+    int             chunks;         /* qr_render(host frame) pipeline depth on one GPU, 0 = automatic */
+    int             pin_frames;     /* QR_B200_PIN_FRAME=1: page-lock the caller's framebuffer on first use */
+    void           *pinned[4];      /* framebuffers registered that way */
     cudaFuncAttributes fattr;
     qr_kpacker      packer;
     char            err[512];
@@ -487,8 +489,12 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         }
     }
 
+    {
+        const char *env = getenv("QR_B200_PIN_FRAME");
+        ctx->pin_frames = env != NULL && env[0] == '1';
+    }
     ctx->shape = QR_DEFAULT_SHAPE;
-    ctx->chunks = 4;
+    ctx->chunks = 0;            /* 0 = automatic */
     {
         const char *env = getenv("QR_B200_CHUNKS");
         if (env != NULL && env[0] >= '1' && env[0] <= '0' + QR_MAX_CHUNKS && env[1] == 0)
@@ -522,6 +528,10 @@ extern "C" void qr_shutdown(qr_ctx *ctx)
     if (ctx == NULL)
     {
         return;
+    }
+    for (int k = 0; k < 4; k++)
+    {
+        if (ctx->pinned[k] != NULL) cudaHostUnregister(ctx->pinned[k]);
     }
     for (int i = 0; i < ctx->ndev; i++)
     {
@@ -929,6 +939,25 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
             direct = true;
         }
         cudaGetLastError();
+        if (!direct && ctx->pin_frames)
+        {
+            /* an application framebuffer lives as long as the scene: page-lock
+             * it once (RooT's XShm image, core_test's frame) */
+            for (int k = 0; k < 4 && !direct; k++)
+            {
+                if (ctx->pinned[k] == NULL)
+                {
+                    const size_t bytes = ((size_t)stride * (h.y_res - 1) + h.x_res) * sizeof(uint32_t);
+                    if (cudaHostRegister(frame, bytes, cudaHostRegisterDefault) == cudaSuccess)
+                    {
+                        ctx->pinned[k] = frame;
+                        direct = true;
+                    }
+                    cudaGetLastError();
+                    break;
+                }
+            }
+        }
     }
     if (!direct)
     {
@@ -944,8 +973,12 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     const size_t wbytes = (size_t)h.x_res * sizeof(uint32_t);
 
     /* chunks of tile rows: the D2H (and the host copy out of staging) of
-     * chunk k overlaps the rendering of chunk k + 1 */
-    int nch = ctx->ndev == 1 ? ctx->chunks : 1;
+     * chunk k overlaps the rendering of chunk k + 1.  Every chunk boundary
+     * drains the GPU once, which costs more than the 0.2 ms D2H of a 1080p
+     * frame it could hide (measured: tools/e2e_breakdown.py), so a
+     * page-locked frame is rendered in one piece; with staging, two chunks
+     * hide half of the host-side copy. */
+    int nch = ctx->ndev == 1 ? (ctx->chunks > 0 ? ctx->chunks : (direct ? 1 : 2)) : 1;
     if (nch > h.tls_col) nch = h.tls_col;
     if (nch < 1) nch = 1;
 
