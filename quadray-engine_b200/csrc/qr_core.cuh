@@ -615,6 +615,8 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
             continue;
         }
 
+        bool reset = (w & (QR_KF_CLOSE | QR_KF_OWNTRM)) != 0;
+
         do
         {
             const uint32_t so = QR_K_SURF_OFF(w);
@@ -654,17 +656,13 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 x5 = qr_mul(x5, x1);
                 x3 = qr_mul(x3, x3);
                 x3 = qr_sub(x3, x5);
-                if (!(0.0f <= x3))
-                {
-                    /* AR_skp: continue behind the array's last leaf */
-                    ni = (uint32_t)e.aux;
-                    en = ea;
-                    if (w & QR_KF_SKIPCLOSE)
-                    {
-                        bo0 = ox; bo1 = oy; bo2 = oz;
-                        cr0 = rx; cr1 = ry; cr2 = rz;
-                    }
-                }
+                /* AR_skp: on a miss continue behind the array's last leaf
+                 * (selects, not a branch: this is the hottest decision) */
+                const bool miss = !(0.0f <= x3);
+                ni = miss ? (uint32_t)e.aux : ni;
+                en.w = miss ? ea.w : en.w;
+                en.aux = miss ? ea.aux : en.aux;
+                reset = miss && (w & QR_KF_SKIPCLOSE) != 0;
                 break;
             }
 
@@ -854,12 +852,10 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
         }
         while (0);
 
-        if (w & (QR_KF_CLOSE | QR_KF_OWNTRM))
-        {
-            /* last element of the open transform node / own matrix: back to the world */
-            bo0 = ox; bo1 = oy; bo2 = oz;
-            cr0 = rx; cr1 = ry; cr2 = rz;
-        }
+        /* after the last element of the open transform node / an own matrix:
+         * back to the world (predicated moves) */
+        bo0 = reset ? ox : bo0; bo1 = reset ? oy : bo1; bo2 = reset ? oz : bo2;
+        cr0 = reset ? rx : cr0; cr1 = reset ? ry : cr1; cr2 = reset ? rz : cr2;
         ei = ni;
         e = en;
     }
