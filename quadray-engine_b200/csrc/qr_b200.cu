@@ -2,13 +2,15 @@
  * qr_b200.cu -- sm_100a kernels and the C ABI of libquadray_b200.so.
  *
  * Kernel qr_render_kernel: a persistent grid (resident CTAs x SM count) whose
- * WARPS pull work from a device-side tile queue.  A work item is one row of
+ * WARPS pull work from a device-side tile queue.  A work item is one band of
  * one screen tile (tile = tile_w x tile_h pixels, core/engine/engine.h:38-39):
- * the warp walks the row in packets of 32 samples -- 32 >> fsaa adjacent
- * pixels times 1 << fsaa samples, the very lane layout of the reference's
- * widest packets (core/engine/engine.cpp:3465-3550) -- so all 32 rays of a
- * warp share the tile's surface list.  This replaces the scanline interleave
- * across worker threads (core/tracer/tracer.cpp:1142-1151, 5383-5394).
+ * the warp walks the band in packets of 32 samples -- a block of 4 x (8 >> fsaa)
+ * pixels times 1 << fsaa samples, in the lane order of the reference's packets
+ * (core/engine/engine.cpp:3465-3550) -- so all 32 rays of a warp share the
+ * tile's surface list and start next to each other on the screen in BOTH
+ * directions (a 4 x 2 pixel block at 4xAA diverges less than 8 x 1).  This
+ * replaces the scanline interleave across worker threads
+ * (core/tracer/tracer.cpp:1142-1151, 5383-5394).
  *
  * Scene staging: header + surfaces + materials + lights (the blob prefix up to
  * the list elements) are copied into shared memory once per CTA with one TMA
@@ -162,13 +164,14 @@ qr_render_kernel(const qr_launch p)
 
     const qr_blob_header &h = *v.h;
     const int fsaa  = h.fsaa;
-    const int ppk   = 32 >> fsaa;                   /* pixels per packet */
+    const int bh    = 8 >> fsaa;                    /* a packet is a block of 4 x bh pixels */
     const int x_res = h.x_res, y_res = h.y_res;
     const int tiles_x = h.tls_row;
     const int tile_w = h.tile_w, tile_h = h.tile_h;
-    const int pk_per_row = (tile_w + ppk - 1) / ppk; /* packets per tile row */
+    const int pk_per_row = (tile_w + 3) / 4;        /* blocks per band of a tile */
+    const int bands = (tile_h + bh - 1) / bh;       /* bands of bh rows per tile */
     const unsigned int n_items =
-        (unsigned int)p.n_trows * (unsigned int)tiles_x * (unsigned int)tile_h;
+        (unsigned int)p.n_trows * (unsigned int)tiles_x * (unsigned int)bands;
 
     /* lane -> (pixel within packet, sample, AA pattern slot), engine.cpp:3465-3550 */
     const int lpx   = lane >> fsaa;
@@ -194,21 +197,26 @@ qr_render_kernel(const qr_launch p)
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= n_items) break;
 
-        const int row  = (int)(item % (unsigned int)tile_h);
-        const int tile = (int)(item / (unsigned int)tile_h);
+        const int brow = (int)(item % (unsigned int)bands);
+        const int tile = (int)(item / (unsigned int)bands);
         const int ty   = p.ty0 + (tile / tiles_x) * p.ty_step;
         const int tx   = tile % tiles_x;
-        const int y    = ty * tile_h + row;
-        if (y >= y_res) continue;
+        const int y0   = ty * tile_h + brow * bh;   /* first row of the block */
+        if (y0 >= y_res) continue;
+        const int y    = y0 + (lpx >> 2);
+        /* rows of this band that exist (inside the tile and the frame) */
+        int rows = tile_h - brow * bh;
+        if (rows > bh) rows = bh;
+        if (rows > y_res - y0) rows = y_res - y0;
 
         for (int pk = 0; pk < pk_per_row; pk++)
         {
-            const int x0 = tx * tile_w + pk * ppk;  /* first pixel of the packet */
+            const int x0 = tx * tile_w + pk * 4;    /* first pixel column of the block */
             if (x0 >= x_res) break;
-            const int px = x0 + lpx;
+            const int px = x0 + (lpx & 3);
 
             float col[3] = {0.0f, 0.0f, 0.0f};
-            const bool live = px < x_res;
+            const bool live = px < x_res && (lpx >> 2) < rows;
             if (live)
             {
                 qr_trace_sample<STAGED>(v, px, y, lane4, stack, sc, col[0], col[1], col[2]);
@@ -241,19 +249,20 @@ qr_render_kernel(const qr_launch p)
             }
             const uint32_t pix = qr_pack(h, r, g, b);
 
-            /* pixel q of the packet sits in lane q << fsaa; lanes 0..ppk/4-1
-             * collect four pixels each and issue one 128-bit store */
+            /* pixel q of the block (row q >> 2, column q & 3) sits in lane
+             * q << fsaa; lanes 0..bh-1 collect the four pixels of one block
+             * row each and issue one 128-bit store */
             uint32_t q4[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
             {
                 q4[j] = __shfl_sync(0xFFFFFFFFu, pix, (((lane << 2) + j) << fsaa) & 31);
             }
-            if (lane < (ppk >> 2))
+            if (lane < rows)
             {
-                const int xq = x0 + (lane << 2);
-                uint32_t *dst = p.frame + (size_t)y * p.stride + xq;
-                if (xq + 3 < x_res && ((((size_t)y * p.stride + xq) & 3) == 0))
+                const int xq = x0;
+                uint32_t *dst = p.frame + (size_t)(y0 + lane) * p.stride + xq;
+                if (xq + 3 < x_res && ((((size_t)(y0 + lane) * p.stride + xq) & 3) == 0))
                 {
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
                 }
@@ -727,7 +736,9 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     p.rays = d.rays_d;
     p.t_out = t_out;
 
-    const unsigned int n_items = (unsigned int)n * ctx->hdr.tls_row * ctx->hdr.tile_h;
+    const int bh = 8 >> ctx->hdr.fsaa;
+    const unsigned int n_items = (unsigned int)n * ctx->hdr.tls_row
+                               * (unsigned int)((ctx->hdr.tile_h + bh - 1) / bh);
     unsigned int grid = (unsigned int)(d.sm_count * d.ctas_per_sm);
     const int threads = g_shapes[ctx->shape].threads;
     const unsigned int warps = (unsigned int)threads / 32u;

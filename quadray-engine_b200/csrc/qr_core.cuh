@@ -314,6 +314,65 @@ QR_HD void qr_xform(const qr_f4 q5, const qr_f4 q6, const float tck_z, uint32_t 
 }
 
 /*
+ * Conic singularity solver, tracer.cpp:1706-1856, for one sample whose
+ * determinant is near zero (lane semantics: hmask decides): a local hit point
+ * closer than t_eps to the apex of a cone / zero hyperboloid / zero
+ * hypercylinder is moved onto the surface next to it.
+ */
+template <bool SH>
+QR_HD void qr_conic_fix(const qr_view<SH> &v, uint32_t so, uint32_t d,
+                        float ld0, float ld1, float ld2, uint32_t amask, int side,
+                        float &lx, float &ly, float &lz)
+{
+    const uint32_t conic = QR_D_CONIC(d);
+    const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
+    const qr_f4 q1 = QR_SURF(v, so, 1);
+    const float t_eps = QR_SURF(v, so, 7).z;
+    const float li = qr_pick3(iI, lx, ly, lz), lj = qr_pick3(iJ, lx, ly, lz), lk = qr_pick3(iK, lx, ly, lz);
+    float a0 = qr_mul(li, li);
+    if (conic != 2)
+    {
+        a0 = qr_add(a0, qr_mul(lj, lj));
+    }
+    a0 = qr_add(a0, qr_mul(lk, lk));
+    if (a0 < t_eps)
+    {
+        const float dfi = qr_pick3(iI, ld0, ld1, ld2), dfj = qr_pick3(iJ, ld0, ld1, ld2), dfk = qr_pick3(iK, ld0, ld1, ld2);
+        const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_j = qr_pick3(iJ, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
+        const uint32_t u1 = (qr_f2u(dfi) & 0x80000000u) ^ 0x3F800000u;
+        uint32_t u2 = 0;
+        float q3 = sci_i;
+        float q4 = 1.0f;
+        if (conic != 2)
+        {
+            u2 = (qr_f2u(dfj) & 0x80000000u) ^ 0x3F800000u;
+            q3 = qr_add(q3, sci_j);
+            q4 = qr_add(q4, 1.0f);
+        }
+        q3 = qr_div(q3, sci_k);
+        q3 = qr_neg(q3);
+        float q6 = q3;
+        q3 = qr_sqrt(q3);
+        q6 = qr_add(q6, q4);
+        q4 = qr_rsq(q6);
+        q4 = qr_mul(q4, t_eps);
+        const float p1 = qr_mul(qr_u2f(u1), q4);
+        const float p2 = qr_mul(qr_u2f(u2), q4);
+        const float p3 = qr_mul(q3, q4);
+        const uint32_t ts = side ? 0x80000000u : 0u;
+        uint32_t u3 = qr_f2u(p3) ^ (qr_f2u(dfk) & 0x80000000u);
+        u3 ^= (ts & amask) ^ amask;
+        const uint32_t tsn = (ts | amask) ^ amask;
+        qr_put3(iI, qr_u2f(qr_f2u(p1) ^ tsn), lx, ly, lz);
+        if (conic != 2)
+        {
+            qr_put3(iJ, qr_u2f(qr_f2u(p2) ^ tsn), lx, ly, lz);
+        }
+        qr_put3(iK, qr_u2f(u3), lx, ly, lz);
+    }
+}
+
+/*
  * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of the surface at
  * "so" (descriptor "d", first quad "q0") that already passed the depth tests
  * t_buf > t and t_min < t (1602-1610).  (lr, ld) are the ray / diff in the
@@ -347,52 +406,7 @@ QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0
     /* conic singularity solver 1706-1856 (lane semantics: hmask decides) */
     if ((d & QR_D_CONIC_MASK) && dmask)
     {
-        const uint32_t conic = QR_D_CONIC(d);
-        const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
-        const qr_f4 q1 = QR_SURF(v, so, 1);
-        const float t_eps = QR_SURF(v, so, 7).z;
-        const float li = qr_pick3(iI, lx, ly, lz), lj = qr_pick3(iJ, lx, ly, lz), lk = qr_pick3(iK, lx, ly, lz);
-        float a0 = qr_mul(li, li);
-        if (conic != 2)
-        {
-            a0 = qr_add(a0, qr_mul(lj, lj));
-        }
-        a0 = qr_add(a0, qr_mul(lk, lk));
-        if (a0 < t_eps)
-        {
-            const float dfi = qr_pick3(iI, ld0, ld1, ld2), dfj = qr_pick3(iJ, ld0, ld1, ld2), dfk = qr_pick3(iK, ld0, ld1, ld2);
-            const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_j = qr_pick3(iJ, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
-            const uint32_t u1 = (qr_f2u(dfi) & 0x80000000u) ^ 0x3F800000u;
-            uint32_t u2 = 0;
-            float q3 = sci_i;
-            float q4 = 1.0f;
-            if (conic != 2)
-            {
-                u2 = (qr_f2u(dfj) & 0x80000000u) ^ 0x3F800000u;
-                q3 = qr_add(q3, sci_j);
-                q4 = qr_add(q4, 1.0f);
-            }
-            q3 = qr_div(q3, sci_k);
-            q3 = qr_neg(q3);
-            float q6 = q3;
-            q3 = qr_sqrt(q3);
-            q6 = qr_add(q6, q4);
-            q4 = qr_rsq(q6);
-            q4 = qr_mul(q4, t_eps);
-            const float p1 = qr_mul(qr_u2f(u1), q4);
-            const float p2 = qr_mul(qr_u2f(u2), q4);
-            const float p3 = qr_mul(q3, q4);
-            const uint32_t ts = side ? 0x80000000u : 0u;
-            uint32_t u3 = qr_f2u(p3) ^ (qr_f2u(dfk) & 0x80000000u);
-            u3 ^= (ts & amask) ^ amask;
-            const uint32_t tsn = (ts | amask) ^ amask;
-            qr_put3(iI, qr_u2f(qr_f2u(p1) ^ tsn), lx, ly, lz);
-            if (conic != 2)
-            {
-                qr_put3(iJ, qr_u2f(qr_f2u(p2) ^ tsn), lx, ly, lz);
-            }
-            qr_put3(iK, qr_u2f(u3), lx, ly, lz);
-        }
+        qr_conic_fix<SH>(v, so, d, ld0, ld1, ld2, amask, side, lx, ly, lz);
     }
 
     /* axis min/max 1874-1927; an axis that is switched off holds -inf / +inf

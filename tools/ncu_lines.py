@@ -22,8 +22,12 @@ kname = rows[0][1]
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
-m = re.match(r"void (\w+)<\(bool\)(\d), \(int\)(\d+), \(int\)(\d+)>", kname)
-mangled = "_Z16%sILb%sELi%sELi%sEEv9qr_launch" % (m.group(1), m.group(2), m.group(3), m.group(4))
+m = re.match(r"void (\w+)<\(bool\)(\d), \(int\)(\d+), \(int\)(\d+)(?:, \(int\)(\d+))?>", kname)
+if m.group(5) is None:
+    mangled = "_Z%d%sILb%sELi%sELi%sEEv9qr_launch" % (len(m.group(1)), m.group(1), m.group(2), m.group(3), m.group(4))
+else:
+    mangled = "_Z%d%sILb%sELi%sELi%sELi%sEEv9qr_launch" % (len(m.group(1)), m.group(1), m.group(2), m.group(3),
+                                                          m.group(4), m.group(5))
 
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, check=True,
@@ -36,7 +40,8 @@ LEAF = (52, 216)    # qr_core.cuh: arithmetic / load / select helpers, attribute
 
 
 def is_leaf(f, l):
-    return (f == "qr_core.cuh" and LEAF[0] <= l <= LEAF[1]) or f.endswith(".hpp") or f.endswith(".h")
+    return (f == "qr_core.cuh" and LEAF[0] <= l <= LEAF[1]) or f.endswith(".hpp") or f.endswith(".h") \
+        or (f == "qr_core.cuh" and 280 <= l <= 316)
 
 
 lines = []          # (file, line) per instruction, in order: innermost non-helper frame
