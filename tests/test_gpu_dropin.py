@@ -1,0 +1,72 @@
+"""The drop-in path on a B200: the reference's ENGINE (core/engine, core/system,
+compiled unmodified from /root/reference by quadray-engine_b200/Makefile) linked
+with this repo's replacement tracer translation unit and libquadray_b200.so.
+
+  build/qr_b200_harness   headless stand-in for RooT: rt_Platform + rt_Scene
+                          construct / render / get_frame through the public API
+  build/core_test_b200    the reference's own test/core_test.cpp, unmodified
+
+Both binaries are built in the build container (they need the reference's
+sources) and travel to the GPU box; nothing here reads /root/reference."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+HARNESS = os.path.join(ROOT, "build", "qr_b200_harness")
+CORE_TEST = os.path.join(ROOT, "build", "core_test_b200")
+
+
+def run_harness(args, tmp_path):
+    out = str(tmp_path / "frame.raw")
+    p = subprocess.run([HARNESS] + args + ["-o", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       timeout=600)
+    assert p.returncode == 0, p.stderr.decode()
+    info = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    frame = np.fromfile(out, dtype=np.uint32).reshape(info["y_res"], info["x_res"])
+    return frame, info
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
+@pytest.mark.parametrize("name", ["test01_full", "test14_full_a4", "test17_full_a4", "test16_none_a4",
+                                  "test05_odd", "demo02_a4g", "demo03_a4g"])
+def test_scene_api_renders_the_reference_frame(entry, tmp_path, name):
+    """rt_Scene::render() -> render0 (tracer_b200.cpp) -> flatten -> C ABI ->
+    kernel -> get_frame(): the frame equals the unmodified reference's."""
+    _, ref, meta = entry.load_golden(name)
+    frame, info = run_harness(meta["args"].split(), tmp_path)
+    assert info["simd"] == "512x2v2"                   # what switch0 answers
+    assert frame.shape == ref.shape
+    assert int((frame != ref).sum()) == 0, meta["args"]
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
+def test_scene_api_animation_and_update_phases(tmp_path):
+    """Several frames with the engine's update phases running between them
+    (animated demo scene): the drop-in keeps rendering and frames change."""
+    a, _ = run_harness(["-s", "demo01", "-a", "2", "-f", "1", "-b", "0"], tmp_path)
+    b, _ = run_harness(["-s", "demo01", "-a", "2", "-f", "3", "-b", "0", "-d", "500"], tmp_path)
+    assert a.shape == b.shape and a.any() and b.any()
+    assert int((a != b).sum()) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(CORE_TEST), reason="build/core_test_b200 was not built")
+def test_reference_core_test_passes_on_the_gpu(tmp_path):
+    """test/core_test.cpp, unmodified: 18 scenes, RT_OPTS_NONE vs RT_OPTS_FULL
+    frames compared with its own tolerance (core_test.cpp:96-145)."""
+    (tmp_path / "dump").mkdir()
+    p = subprocess.run([CORE_TEST], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=900)
+    text = p.stdout.decode(errors="replace")
+    assert p.returncode == 0, text[-2000:]
+    # one "Time N" / "Time F" pair per scene, no "Frames differ", no exception
+    assert len(re.findall(r"Time F", text)) == 18, text[-2000:]
+    assert "Frames differ" not in text and "Exception" not in text, text[-2000:]
+    assert "simd =  512x2v2" in text or "512x2v2" in text
