@@ -32,22 +32,21 @@ int32_t qr_Flattener::list_head(const rt_ELEM *head, ListKind kind)
         return QR_NIL;
     }
 
-    std::unordered_map<const void *, int32_t>::iterator it =
-                                                        elem_idx.find(head);
-    if (it != elem_idx.end())
+    int32_t first = elem_idx.find(head);
+    if (first >= 0)
     {
-        return it->second;
+        return first;
     }
 
     /* index the whole chain consecutively, stop at a shared tail */
-    int32_t first = (int32_t)elem_src.size();
+    first = (int32_t)elem_src.size();
     for (const rt_ELEM *e = head; e != RT_NULL; e = e->next)
     {
-        if (elem_idx.find(e) != elem_idx.end())
+        const int32_t next = (int32_t)elem_src.size();
+        if (elem_idx.insert(e, next) != next)
         {
             break;
         }
-        elem_idx[e] = (int32_t)elem_src.size();
         elem_src.push_back(e);
         elem_kind.push_back(kind);
     }
@@ -60,14 +59,12 @@ int32_t qr_Flattener::surface(const rt_SIMD_SURFACE *s)
     {
         return QR_NIL;
     }
-    std::unordered_map<const void *, int32_t>::iterator it = surf_idx.find(s);
-    if (it != surf_idx.end())
+    const int32_t next = (int32_t)surf_src.size();
+    const int32_t idx = surf_idx.insert(s, next);
+    if (idx == next)
     {
-        return it->second;
+        surf_src.push_back(s);
     }
-    int32_t idx = (int32_t)surf_src.size();
-    surf_idx[s] = idx;
-    surf_src.push_back(s);
     return idx;
 }
 
@@ -77,10 +74,10 @@ int32_t qr_Flattener::material(const rt_SIMD_MATERIAL *m)
     {
         return QR_NIL;
     }
-    std::unordered_map<const void *, int32_t>::iterator it = mat_idx.find(m);
-    if (it != mat_idx.end())
+    const int32_t known = mat_idx.find(m);
+    if (known >= 0)
     {
-        return it->second;
+        return known;
     }
 
     qr_material r;
@@ -113,21 +110,17 @@ int32_t qr_Flattener::material(const rt_SIMD_MATERIAL *m)
     {
         throw rt_Exception("null texture pointer in qr_Flattener");
     }
-    std::unordered_map<const void *, int32_t>::iterator tt = tex_idx.find(tex);
-    if (tt != tex_idx.end())
-    {
-        r.tex = tt->second;
-    }
-    else
+    r.tex = tex_idx.find(tex);
+    if (r.tex < 0)
     {
         size_t n = (size_t)(r.xmask + 1) * (size_t)(r.ymask + 1);
         r.tex = (int32_t)texels.size();
-        tex_idx[tex] = r.tex;
+        tex_idx.insert(tex, r.tex);
         texels.insert(texels.end(), tex, tex + n);
     }
 
     int32_t idx = (int32_t)mats.size();
-    mat_idx[m] = idx;
+    mat_idx.insert(m, idx);
     mats.push_back(r);
     return idx;
 }
@@ -138,10 +131,10 @@ int32_t qr_Flattener::light(const rt_SIMD_LIGHT *l)
     {
         return QR_NIL;
     }
-    std::unordered_map<const void *, int32_t>::iterator it = lgt_idx.find(l);
-    if (it != lgt_idx.end())
+    const int32_t known = lgt_idx.find(l);
+    if (known >= 0)
     {
-        return it->second;
+        return known;
     }
 
     qr_light r;
@@ -158,7 +151,7 @@ int32_t qr_Flattener::light(const rt_SIMD_LIGHT *l)
     r.a_cnt  = l->a_cnt[0];
 
     int32_t idx = (int32_t)lgts.size();
-    lgt_idx[l] = idx;
+    lgt_idx.insert(l, idx);
     lgts.push_back(r);
     return idx;
 }
@@ -278,7 +271,10 @@ void qr_Flattener::drain()
     for (size_t i = 0; i < elems.size(); i++)
     {
         const rt_ELEM *n = elem_src[i]->next;
-        elems[i].next = n == RT_NULL ? QR_NIL : elem_idx[n];
+        /* chains are indexed consecutively: the successor is nearly always i + 1 */
+        elems[i].next = n == RT_NULL ? QR_NIL
+                      : (i + 1 < elems.size() && elem_src[i + 1] == n) ? (int32_t)(i + 1)
+                      : elem_idx.find(n);
     }
 }
 
@@ -303,7 +299,12 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
 
     elem_idx.clear(); surf_idx.clear(); mat_idx.clear();
     lgt_idx.clear();  tex_idx.clear();
-    elem_src.clear(); elem_kind.clear(); surf_src.clear();
+    {
+        /* last frame's sizes are the best guess for this frame's */
+        const size_t ne = elem_src.size() + 1024;
+        elem_src.clear(); elem_kind.clear(); surf_src.clear();
+        elem_src.reserve(ne); elem_kind.reserve(ne); elems.reserve(ne);
+    }
     elems.clear(); surfs.clear(); mats.clear(); lgts.clear();
     texels.clear(); tiles.clear();
     surf_done = 0;
@@ -388,7 +389,22 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     h.off_texels = off; off = align16(off + h.n_texels * sizeof(uint32_t));
     h.total_bytes = off;
 
-    blob.assign(off, 0);
+    blob.resize(off);
+    {
+        /* the sections are copied below; only the alignment gaps need zeroing */
+        const uint32_t ends[7] = { (uint32_t)sizeof(h),
+            h.off_surf   + h.n_surf   * (uint32_t)sizeof(qr_surface),
+            h.off_mat    + h.n_mat    * (uint32_t)sizeof(qr_material),
+            h.off_lgt    + h.n_lgt    * (uint32_t)sizeof(qr_light),
+            h.off_elem   + h.n_elem   * (uint32_t)sizeof(qr_elem),
+            h.off_tiles  + h.n_tiles  * (uint32_t)sizeof(int32_t),
+            h.off_texels + h.n_texels * (uint32_t)sizeof(uint32_t) };
+        const uint32_t nexts[7] = { h.off_surf, h.off_mat, h.off_lgt, h.off_elem, h.off_tiles, h.off_texels, off };
+        for (int k = 0; k < 7; k++)
+        {
+            if (nexts[k] > ends[k]) memset(&blob[ends[k]], 0, nexts[k] - ends[k]);
+        }
+    }
     memcpy(&blob[0], &h, sizeof(h));
     if (h.n_surf)   memcpy(&blob[h.off_surf],   &surfs[0],  h.n_surf   * sizeof(qr_surface));
     if (h.n_mat)    memcpy(&blob[h.off_mat],    &mats[0],   h.n_mat    * sizeof(qr_material));

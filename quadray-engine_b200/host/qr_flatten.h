@@ -15,7 +15,6 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <vector>
-#include <unordered_map>
 
 #include "qr_scene_blob.h"
 
@@ -24,6 +23,88 @@ struct rt_SIMD_SURFACE;
 struct rt_SIMD_MATERIAL;
 struct rt_SIMD_LIGHT;
 struct rt_ELEM;
+
+/*
+ * Pointer -> index map for one frame: open addressing, no allocation once
+ * warm, cleared in O(1) by bumping a generation stamp (the flattener runs
+ * every frame inside render0, on ~20 k list elements for the demo scenes).
+ */
+class qr_PtrMap
+{
+    public:
+
+    qr_PtrMap() : gen(1), used(0) {}
+
+    void clear()
+    {
+        gen++;
+        used = 0;
+        if (gen == 0)                           /* stamp wrapped: really clear */
+        {
+            stamp.assign(stamp.size(), 0);
+            gen = 1;
+        }
+    }
+
+    /* index stored for "p", or -1 */
+    int32_t find(const void *p) const
+    {
+        if (keys.empty()) return -1;
+        const size_t mask = keys.size() - 1;
+        for (size_t i = hash(p) & mask; ; i = (i + 1) & mask)
+        {
+            if (stamp[i] != gen) return -1;
+            if (keys[i] == p) return vals[i];
+        }
+    }
+
+    /* store "v" for "p" unless present; returns the stored index */
+    int32_t insert(const void *p, int32_t v)
+    {
+        if ((used + 1) * 2 > keys.size()) grow();
+        const size_t mask = keys.size() - 1;
+        for (size_t i = hash(p) & mask; ; i = (i + 1) & mask)
+        {
+            if (stamp[i] != gen)
+            {
+                stamp[i] = gen; keys[i] = p; vals[i] = v;
+                used++;
+                return v;
+            }
+            if (keys[i] == p) return vals[i];
+        }
+    }
+
+    private:
+
+    static size_t hash(const void *p)
+    {
+        /* the engine bump-allocates its records, so neighbours in memory are
+         * neighbours in a list: keep that locality in the table */
+        const uintptr_t u = (uintptr_t)p >> 5;
+        return (size_t)(u ^ (u >> 17));
+    }
+
+    void grow()
+    {
+        std::vector<const void *> ok; std::vector<int32_t> ov; std::vector<uint32_t> os;
+        ok.swap(keys); ov.swap(vals); os.swap(stamp);
+        const size_t n = ok.empty() ? 1024 : ok.size() * 2;
+        keys.assign(n, (const void *)0); vals.assign(n, 0); stamp.assign(n, 0);
+        const uint32_t g = gen;
+        used = 0;
+        for (size_t i = 0; i < ok.size(); i++)
+        {
+            if (os[i] == g) insert(ok[i], ov[i]);
+        }
+    }
+
+    std::vector<const void *> keys;
+    std::vector<int32_t>      vals;
+    std::vector<uint32_t>     stamp;
+    uint32_t                  gen;
+    size_t                    used;
+};
 
 class qr_Flattener
 {
@@ -45,8 +126,7 @@ class qr_Flattener
     int32_t     light(const rt_SIMD_LIGHT *l);
     void        drain();
 
-    std::unordered_map<const void *, int32_t> elem_idx, surf_idx, mat_idx,
-                                              lgt_idx, tex_idx;
+    qr_PtrMap   elem_idx, surf_idx, mat_idx, lgt_idx, tex_idx;
     std::vector<const rt_ELEM *>            elem_src;
     std::vector<ListKind>                   elem_kind;
     std::vector<const rt_SIMD_SURFACE *>    surf_src;

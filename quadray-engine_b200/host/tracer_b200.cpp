@@ -25,6 +25,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <sys/time.h>
 
 #include "tracer.h"
 #include "format.h"
@@ -84,6 +85,13 @@ rt_si32 rt_Platform::switch0(rt_SIMD_INFOX *s_inf, rt_si32 simd)
 static qr_ctx      *g_ctx = RT_NULL;
 static qr_Flattener g_flat;
 static char         g_err[600];
+
+static double qr_now_ms()
+{
+    timeval tm;
+    gettimeofday(&tm, NULL);
+    return tm.tv_sec * 1000.0 + tm.tv_usec / 1000.0;
+}
 
 static rt_void qr_throw(rt_pstr what, const qr_ctx *ctx)
 {
@@ -152,16 +160,30 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
 
     qr_context();
 
+    /* QR_B200_TIMING=1: wall time of the three steps, every 64th frame, on
+     * stderr in the style of the reference's "Time" lines */
+    static const bool timing = getenv("QR_B200_TIMING") != RT_NULL;
+    static unsigned frame_no = 0;
+    const double t0 = timing ? qr_now_ms() : 0.0;
+
     size_t bytes = 0;
     const uint8_t *blob = g_flat.build(s_inf, &bytes);
+    const double t1 = timing ? qr_now_ms() : 0.0;
 
     if (qr_scene_upload(g_ctx, blob, bytes) != QR_OK)
     {
         qr_throw("B200 scene upload failed", g_ctx);
     }
+    const double t2 = timing ? qr_now_ms() : 0.0;
     if (qr_render(g_ctx, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
     {
         qr_throw("B200 render failed", g_ctx);
+    }
+    if (timing && (frame_no++ & 63) == 8)
+    {
+        const double t3 = qr_now_ms();
+        fprintf(stderr, "B200 render0: flatten %.3f ms, upload %.3f ms, render + frame copy %.3f ms "
+                        "(blob %u bytes)\n", t1 - t0, t2 - t1, t3 - t2, (unsigned)bytes);
     }
 }
 
