@@ -170,8 +170,8 @@ qr_render_kernel(const qr_launch p)
     const int tile_w = h.tile_w, tile_h = h.tile_h;
     const int pk_per_row = (tile_w + 3) / 4;        /* blocks per band of a tile */
     const int bands = (tile_h + bh - 1) / bh;       /* bands of bh rows per tile */
-    const unsigned int n_items =
-        (unsigned int)p.n_trows * (unsigned int)tiles_x * (unsigned int)bands;
+    const unsigned int per_tile = (unsigned int)bands * (unsigned int)pk_per_row;
+    const unsigned int n_items = (unsigned int)p.n_trows * (unsigned int)tiles_x * per_tile;
 
     /* lane -> (pixel within packet, sample, AA pattern slot), engine.cpp:3465-3550 */
     const int lpx   = lane >> fsaa;
@@ -190,29 +190,33 @@ qr_render_kernel(const qr_launch p)
     asm volatile("mov.u32 %0, %0;" : "+r"(sc.addr));
     qr_sc_st(sc, QR_SC_MISC, 0.0f, 0.0f, 0.0f, 0.0f);
 
-    for (;;)
-    {
-        unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(p.queue, 1u);
-        item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        if (item >= n_items) break;
+    /* one work item = one packet (a 4 x bh pixel block of a tile); the queue
+     * is read one item ahead, so the atomic's latency hides behind a trace */
+    unsigned int item = 0;
+    if (lane == 0) item = atomicAdd(p.queue, 1u);
+    item = __shfl_sync(0xFFFFFFFFu, item, 0);
 
-        const int brow = (int)(item % (unsigned int)bands);
-        const int tile = (int)(item / (unsigned int)bands);
-        const int ty   = p.ty0 + (tile / tiles_x) * p.ty_step;
-        const int tx   = tile % tiles_x;
+    while (item < n_items)
+    {
+        unsigned int next = 0;
+        if (lane == 0) next = atomicAdd(p.queue, 1u);
+
+        const unsigned int tile = item / per_tile;
+        const unsigned int sub  = item % per_tile;
+        const int brow = (int)(sub / (unsigned int)pk_per_row);
+        const int pk   = (int)(sub % (unsigned int)pk_per_row);
+        const int ty   = p.ty0 + (int)(tile / (unsigned int)tiles_x) * p.ty_step;
+        const int tx   = (int)(tile % (unsigned int)tiles_x);
         const int y0   = ty * tile_h + brow * bh;   /* first row of the block */
-        if (y0 >= y_res) continue;
+        const int x0   = tx * tile_w + pk * 4;      /* first pixel column of the block */
         const int y    = y0 + (lpx >> 2);
         /* rows of this band that exist (inside the tile and the frame) */
         int rows = tile_h - brow * bh;
         if (rows > bh) rows = bh;
         if (rows > y_res - y0) rows = y_res - y0;
 
-        for (int pk = 0; pk < pk_per_row; pk++)
+        if (y0 < y_res && x0 < x_res)
         {
-            const int x0 = tx * tile_w + pk * 4;    /* first pixel column of the block */
-            if (x0 >= x_res) break;
             const int px = x0 + (lpx & 3);
 
             float col[3] = {0.0f, 0.0f, 0.0f};
@@ -275,6 +279,7 @@ qr_render_kernel(const qr_launch p)
                 }
             }
         }
+        item = __shfl_sync(0xFFFFFFFFu, next, 0);
     }
 
     /* ray counters: warp-reduce, one atomic per warp and kind */
@@ -738,7 +743,8 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
 
     const int bh = 8 >> ctx->hdr.fsaa;
     const unsigned int n_items = (unsigned int)n * ctx->hdr.tls_row
-                               * (unsigned int)((ctx->hdr.tile_h + bh - 1) / bh);
+                               * (unsigned int)((ctx->hdr.tile_h + bh - 1) / bh)
+                               * (unsigned int)((ctx->hdr.tile_w + 3) / 4);
     unsigned int grid = (unsigned int)(d.sm_count * d.ctas_per_sm);
     const int threads = g_shapes[ctx->shape].threads;
     const unsigned int warps = (unsigned int)threads / 32u;

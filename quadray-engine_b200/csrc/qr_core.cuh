@@ -43,10 +43,14 @@
 
 #if defined(__CUDACC__)
 #define QR_HD __host__ __device__ __forceinline__
+/* paths that are rare in most scenes live out of line, so that the hot list
+ * walk stays compact in the instruction cache */
+#define QR_HD_COLD __host__ __device__ __noinline__
 #else
 #include <math.h>
 #include <string.h>
 #define QR_HD static inline
+#define QR_HD_COLD static
 #endif
 
 /* ---- rounded arithmetic ---------------------------------------------------- */
@@ -320,10 +324,11 @@ QR_HD void qr_xform(const qr_f4 q5, const qr_f4 q6, const float tck_z, uint32_t 
  * hypercylinder is moved onto the surface next to it.
  */
 template <bool SH>
-QR_HD void qr_conic_fix(const qr_view<SH> &v, uint32_t so, uint32_t d,
-                        float ld0, float ld1, float ld2, uint32_t amask, int side,
-                        float &lx, float &ly, float &lz)
+QR_HD_COLD qr_f4 qr_conic_fix(const typename qr_hot<SH>::base_t surf, uint32_t so, uint32_t d,
+                              float ld0, float ld1, float ld2, uint32_t amask, int side,
+                              float lx, float ly, float lz)
 {
+    struct { typename qr_hot<SH>::base_t surf; } v = { surf };
     const uint32_t conic = QR_D_CONIC(d);
     const uint32_t iI = QR_D_MAP(d, 0), iJ = QR_D_MAP(d, 1), iK = QR_D_MAP(d, 2);
     const qr_f4 q1 = QR_SURF(v, so, 1);
@@ -370,60 +375,24 @@ QR_HD void qr_conic_fix(const qr_view<SH> &v, uint32_t so, uint32_t d,
         }
         qr_put3(iK, qr_u2f(u3), lx, ly, lz);
     }
+    qr_f4 r;
+    r.x = lx; r.y = ly; r.z = lz; r.w = 0.0f;
+    return r;
 }
 
 /*
- * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of the surface at
- * "so" (descriptor "d", first quad "q0") that already passed the depth tests
- * t_buf > t and t_min < t (1602-1610).  (lr, ld) are the ray / diff in the
- * surface's field set (world or trnode space).  On success lx/ly/lz hold the
- * (possibly adjusted) local hit point.
+ * Custom clippers of a surface, tracer.cpp:1931-2151, for one candidate hit:
+ * (hx, hy, hz) is the hit point in the world, (lx, ly, lz) in the surface's
+ * space, (q0x, q0y, q0z) the surface's position.  Out of line (see
+ * QR_HD_COLD); the view's members it needs come by value.
  */
 template <bool SH>
-QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0,
-                   float ox, float oy, float oz, float rx, float ry, float rz,
-                   float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
-                   float t, bool dmask, uint32_t amask, int side,
-                   float &lx, float &ly, float &lz)
+QR_HD_COLD bool qr_clip_custom(const typename qr_hot<SH>::base_t surf, const qr_kelem *elems, uint32_t so,
+                               float q0x, float q0y, float q0z, float hx, float hy, float hz,
+                               float lx, float ly, float lz)
 {
-    const float hx = qr_add(qr_mul(rx, t), ox);
-    const float hy = qr_add(qr_mul(ry, t), oy);
-    const float hz = qr_add(qr_mul(rz, t), oz);
-
-    if (d & QR_D_TRM_MASK)
-    {
-        lx = qr_add(qr_mul(lr0, t), ld0);
-        ly = qr_add(qr_mul(lr1, t), ld1);
-        lz = qr_add(qr_mul(lr2, t), ld2);
-    }
-    else
-    {
-        lx = qr_sub(hx, q0.x);
-        ly = qr_sub(hy, q0.y);
-        lz = qr_sub(hz, q0.z);
-    }
-
-    /* conic singularity solver 1706-1856 (lane semantics: hmask decides) */
-    if ((d & QR_D_CONIC_MASK) && dmask)
-    {
-        qr_conic_fix<SH>(v, so, d, ld0, ld1, ld2, amask, side, lx, ly, lz);
-    }
-
-    /* axis min/max 1874-1927; an axis that is switched off holds -inf / +inf
-     * (qr_kscene.h), so all six compares run unconditionally */
-    if (d & QR_D_MM_MASK)
-    {
-        const qr_f4 q3 = QR_SURF(v, so, 3), q4 = QR_SURF(v, so, 4);
-        const bool m = (q3.x <= lx) && (q3.y <= ly) && (q3.z <= lz)
-                    && qr_ge(q4.x, lx) && qr_ge(q4.y, ly) && qr_ge(q4.z, lz);
-        if (!m) return false;
-    }
-
-    if (!(d & QR_D_HASCLIP_MASK))
-    {
-        return true;
-    }
-
+    struct { typename qr_hot<SH>::base_t surf; const qr_kelem *elems; } v = { surf, elems };
+    struct { float x, y, z; } q0 = { q0x, q0y, q0z };
     /* custom clippers 1931-2151.  The reference evaluates the whole list for
      * the packet; a lone sample may stop as soon as its mask is clear and no
      * accumulator is open (a cleared mask can only come back through an
@@ -541,6 +510,62 @@ QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0
         m = m && last;
     }
     return m;
+}
+
+/*
+ * CC_clp, tracer.cpp:1597-2160, for one candidate root "t" of the surface at
+ * "so" (descriptor "d", first quad "q0") that already passed the depth tests
+ * t_buf > t and t_min < t (1602-1610).  (lr, ld) are the ray / diff in the
+ * surface's field set (world or trnode space).  On success lx/ly/lz hold the
+ * (possibly adjusted) local hit point.
+ */
+template <bool SH>
+QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0,
+                   float ox, float oy, float oz, float rx, float ry, float rz,
+                   float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
+                   float t, bool dmask, uint32_t amask, int side,
+                   float &lx, float &ly, float &lz)
+{
+    const float hx = qr_add(qr_mul(rx, t), ox);
+    const float hy = qr_add(qr_mul(ry, t), oy);
+    const float hz = qr_add(qr_mul(rz, t), oz);
+
+    if (d & QR_D_TRM_MASK)
+    {
+        lx = qr_add(qr_mul(lr0, t), ld0);
+        ly = qr_add(qr_mul(lr1, t), ld1);
+        lz = qr_add(qr_mul(lr2, t), ld2);
+    }
+    else
+    {
+        lx = qr_sub(hx, q0.x);
+        ly = qr_sub(hy, q0.y);
+        lz = qr_sub(hz, q0.z);
+    }
+
+    /* conic singularity solver 1706-1856 (lane semantics: hmask decides) */
+    if ((d & QR_D_CONIC_MASK) && dmask)
+    {
+        const qr_f4 f = qr_conic_fix<SH>(v.surf, so, d, ld0, ld1, ld2, amask, side, lx, ly, lz);
+        lx = f.x; ly = f.y; lz = f.z;
+    }
+
+    /* axis min/max 1874-1927; an axis that is switched off holds -inf / +inf
+     * (qr_kscene.h), so all six compares run unconditionally */
+    if (d & QR_D_MM_MASK)
+    {
+        const qr_f4 q3 = QR_SURF(v, so, 3), q4 = QR_SURF(v, so, 4);
+        const bool m = (q3.x <= lx) && (q3.y <= ly) && (q3.z <= lz)
+                    && qr_ge(q4.x, lx) && qr_ge(q4.y, ly) && qr_ge(q4.z, lz);
+        if (!m) return false;
+    }
+
+    if (!(d & QR_D_HASCLIP_MASK))
+    {
+        return true;
+    }
+
+    return qr_clip_custom<SH>(v.surf, v.elems, so, q0.x, q0.y, q0.z, hx, hy, hz, lx, ly, lz);
 }
 
 /*
