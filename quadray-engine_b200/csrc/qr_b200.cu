@@ -689,7 +689,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     const uint32_t prefix = kh->off_elem;
     const int slots = g_shapes[ctx->shape].threads * QR_SC_QUADS * 16;     /* per-thread scratch quads */
     const int budget = ctx->dev[0].smem_optin - (int)ctx->fattr.sharedSizeBytes - 1024 - slots;
-    if ((prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
+    /* QR_B200_NOSTAGE=1 forces the variant that reads the scene through L1/L2
+     * (what scenes too large for shared memory get) -- for testing */
+    static const bool nostage = getenv("QR_B200_NOSTAGE") != NULL && getenv("QR_B200_NOSTAGE")[0] == '1';
+    if (!nostage && (prefix & 15) == 0 && prefix < (1u << 20) && (int)prefix <= budget)
     {
         ctx->stage_bytes = prefix;
     }

@@ -158,6 +158,29 @@ def test_gpu_render_into_pinned_frame(entry, ctx):
     assert np.array_equal(got[:, :w], ref) and (got[:, w:] == 0xFFFFFFFF).all()
 
 
+def test_gpu_unstaged_scene_variant(entry, pkg):
+    """Scenes too large for shared memory are read through L1/L2 by a second
+    kernel variant; forced here on ordinary fixtures, it renders the same frames."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, __graft_entry__ as ge\n"
+        "pkg = ge.load_package(); c = pkg.Context([0])\n"
+        "for name in ('test14_full_a4', 'test17_full_a4', 'test03_full', 'demo02_a4g'):\n"
+        "    blob, ref, meta = ge.load_golden(name)\n"
+        "    c.upload(blob); got = c.render_frame()\n"
+        "    assert c.kernel_info()['scene_in_smem'] == 0\n"
+        "    assert int((got != ref).sum()) == 0, name\n"
+        "c.close(); print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    env = dict(os.environ)
+    env["QR_B200_NOSTAGE"] = "1"
+    p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=600)
+    assert p.returncode == 0 and b"ok" in p.stdout, p.stdout.decode(errors="replace")[-2000:]
+
+
 def test_gpu_render_is_deterministic(entry, ctx):
     blob, _, _ = entry.load_golden("demo02_a4g")
     ctx.upload(blob)
