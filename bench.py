@@ -433,7 +433,7 @@ def main_gpu(args, rank, world, local_rank):
             "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": UNIT,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "qr_scene_upload(host blob) + qr_render(pinned host frame; chunked render/D2H pipeline)"
+                    "path": "qr_scene_upload(host blob: pack + pinned H2D) + qr_render(page-locked host frame, written by the kernel over PCIe)"
                             if world == 1 else
                             "qr_scene_upload + qr_render_rows + frame exchange (%s) + D2H on rank 0" % gather,
                     "pixels_differ_vs_reference_cpu_frame": e2e_parity},

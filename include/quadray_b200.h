@@ -73,9 +73,11 @@ int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes);
  *   frame  != NULL: host framebuffer of y_res rows, "stride" pixels apart
  *                   (0x00RRGGBB, rt_Scene::get_frame(), engine.cpp:3774-3777);
  *                   the call returns when it holds the finished frame.  On
- *                   one GPU the frame is rendered in a few chunks of tile
- *                   rows whose D2H overlaps the next chunk's rendering; a
- *                   page-locked frame receives the D2H directly.
+ *                   one GPU a page-locked frame (cudaMallocHost /
+ *                   cudaHostRegister, or QR_B200_PIN_FRAME=1) is written by the
+ *                   kernel itself over PCIe while it renders -- no D2H pass;
+ *                   any other frame goes through pinned staging in two chunks
+ *                   whose copy overlaps the rendering of the next.
  *   frame  == NULL: render only (asynchronous; see qr_sync / qr_frame_device).
  */
 int qr_render(qr_ctx *ctx, uint32_t *frame, int stride);

@@ -375,6 +375,7 @@ struct qr_ctx
     int             shape;          /* index into g_shapes */
     int             chunks;         /* qr_render(host frame) pipeline depth on one GPU, 0 = automatic */
     int             pin_frames;     /* QR_B200_PIN_FRAME=1: page-lock the caller's framebuffer on first use */
+    int             zerocopy;       /* store pixels straight into a page-locked host frame (QR_B200_ZEROCOPY=0: off) */
     void           *pinned[4];      /* framebuffers registered that way */
     cudaFuncAttributes fattr;
     qr_kpacker      packer;
@@ -506,6 +507,8 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
     {
         const char *env = getenv("QR_B200_PIN_FRAME");
         ctx->pin_frames = env != NULL && env[0] == '1';
+        env = getenv("QR_B200_ZEROCOPY");
+        ctx->zerocopy = !(env != NULL && env[0] == '0');     /* on unless QR_B200_ZEROCOPY=0 */
     }
     ctx->shape = QR_DEFAULT_SHAPE;
     ctx->chunks = 0;            /* 0 = automatic */
@@ -1001,6 +1004,25 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     int nch = ctx->ndev == 1 ? (ctx->chunks > 0 ? ctx->chunks : (direct ? 1 : 2)) : 1;
     if (nch > h.tls_col) nch = h.tls_col;
     if (nch < 1) nch = 1;
+
+    /* (QR_B200_ZEROCOPY=0 turns this off) a page-locked frame is device-addressable (UVA), so
+     * the kernel can store its pixels straight into host memory; the PCIe
+     * writes then overlap the rendering and there is no D2H pass at all */
+    if (ctx->ndev == 1 && direct && ctx->zerocopy)
+    {
+        uint32_t *dev_view = NULL;
+        if (cudaHostGetDevicePointer((void **)&dev_view, frame, 0) == cudaSuccess && dev_view != NULL)
+        {
+            rc = qr_launch_rows(ctx, 0, dev_view, stride, 0, 1, h.tls_col, NULL);
+            if (rc != QR_OK)
+            {
+                return rc;
+            }
+            QR_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+            return QR_OK;
+        }
+        cudaGetLastError();
+    }
 
     if (ctx->ndev == 1)
     {
