@@ -49,6 +49,8 @@
 #include "scn_test17.h"
 #include "scn_test18.h"
 
+#include "qr_synth_scene.h"
+
 struct SceneEntry { const char *name; rt_SCENE *root; };
 
 static SceneEntry g_scenes[] =
@@ -255,7 +257,8 @@ static rt_void pool_render(rt_pntr tdata, rt_si32 thnum, rt_si32 phase)
 
 static void usage()
 {
-    printf("qr_harness -s <test01..test18|demo01..demo03> [-x w] [-y h]\n"
+    printf("qr_harness -s <test01..test18|demo01..demo03|synth> [-x w] [-y h]\n"
+           "  [synth: -N quadrics -S seed -E extent -R 0|1 (rotations) -M metal_permille]\n"
            "  [-a 0|1|2 (fsaa none/2x/4x)] [-p none|full|default|0xHEX (opts)]\n"
            "  [-g (gamma prop on)] [-r (fresnel prop on)] [-c cam_idx]\n"
            "  [-t threads (0 = stub, sequential)] [-f frames] [-w warmup]\n"
@@ -271,6 +274,7 @@ int main(int argc, char **argv)
     int cam_idx = 0, n_simd = 0, k_size = 0, s_type = 0, quiet = 0;
     int gamma_on = 0, fresnel_on = 0, freeze = 0;
     long t_begin = 0, t_delta = 16;
+    qr_synth::Params synth = { 1000, 1, 100.0f, 1, 0 };
 
     for (int i = 1; i < argc; i++)
     {
@@ -295,6 +299,11 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-v")) { s_type = atoi(v); i++; }
         else if (!strcmp(a, "-o")) { out = v; i++; }
         else if (!strcmp(a, "-q")) { quiet = 1; }
+        else if (!strcmp(a, "-N")) { synth.n = atoi(v); i++; }
+        else if (!strcmp(a, "-S")) { synth.seed = (unsigned)atol(v); i++; }
+        else if (!strcmp(a, "-E")) { synth.extent = (float)atof(v); i++; }
+        else if (!strcmp(a, "-R")) { synth.rotate = atoi(v); i++; }
+        else if (!strcmp(a, "-M")) { synth.metal = atoi(v); i++; }
         else { usage(); return 2; }
     }
 
@@ -307,6 +316,11 @@ int main(int argc, char **argv)
             root = *g_scenes[i].root;
             found = true;
         }
+    }
+    if (!found && !strcmp(scene_name, "synth") && synth.n > 0)
+    {
+        root = qr_synth::build(synth);
+        found = true;
     }
     if (!found)
     {

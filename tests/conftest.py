@@ -17,7 +17,10 @@ _NPZ = sorted(f[:-4] for f in os.listdir(os.path.join(ROOT, "tests", "golden")) 
 # "...h" fixtures (full-size cases of BASELINE.json configs 3 and 4) hold the
 # reference frame as per-row CRC-32s instead of pixels
 GOLDEN_HASHED = [g for g in _NPZ if g.endswith("h")]
-GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h")]
+# "...c" fixtures (config 5 at size) hold row CRC-32s only; the scene comes from
+# the generator inside the harness binaries
+GOLDEN_CRC = [g for g in _NPZ if g.endswith("c")]
+GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h") and not g.endswith("c")]
 # the 1080p frame is the bench workload; CPU tests use the 800x480 cases
 GOLDEN_SMALL = [g for g in GOLDEN_ALL if "1080p" not in g]
 

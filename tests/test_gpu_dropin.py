@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from conftest import GOLDEN_CRC, ROOT
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,23 @@ def test_scene_api_renders_the_reference_frame(entry, tmp_path, name):
     assert info["simd"] == "512x2v2"                   # what switch0 answers
     assert frame.shape == ref.shape
     assert int((frame != ref).sum()) == 0, meta["args"]
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
+@pytest.mark.parametrize("name", GOLDEN_CRC)
+def test_generated_quadric_clouds_at_size(entry, tmp_path, name):
+    """BASELINE.json config 5: 10k / 100k random quadrics under 8-ary
+    bounding-volume arrays (apps/qr_synth_scene.h), up to 7680x4320 4xAA.  The
+    harness generates the scene, the engine builds its lists, the backend
+    flattens and renders; every row of the frame has the CRC-32 of the
+    reference's row (fixture made by tools/make_golden.py from the unmodified
+    reference), i.e. the frames are identical.  The scene does not fit shared
+    memory, so this is also the unstaged (L1/L2) kernel at size."""
+    rowcrc, meta = entry.load_golden_crc(name)
+    frame, info = run_harness(meta["args"].split(), tmp_path)
+    assert frame.shape == (meta["y_res"], meta["x_res"])
+    bad = np.nonzero(entry.row_crcs(frame) != rowcrc)[0]
+    assert bad.size == 0, (meta["args"], bad[:10].tolist())
 
 
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")

@@ -46,6 +46,10 @@ CASES.update({
     "demo02_a4g":     "-s demo02 -a 2 -g",
     "demo03_a4g":     "-s demo03 -a 2 -g -b 1000",
     "demo03_1080p_a4g": "-s demo03 -x 1920 -y 1080 -a 2 -g",
+    # BASELINE.json config 5 in miniature: generated quadric clouds under 8-ary
+    # bounding-volume arrays (apps/qr_synth_scene.h), with and without mirrors
+    "synth1k_a4":     "-s synth -N 1000 -E 25 -x 480 -y 270 -a 2",
+    "synth400_metal": "-s synth -N 400 -E 16 -M 300 -S 7 -x 400 -y 240",
 })
 
 
@@ -62,6 +66,33 @@ CASES_HASHED = {
     "test18_1080p_a4h": "-s test18 -p full -x 1920 -y 1080 -a 2",
     "demo03_4k_a4gh":   "-s demo03 -x 3840 -y 2160 -a 2 -g",
 }
+
+
+# Config 5 at size: only the reference frame's row CRC-32s are kept ("c"
+# suffix, no blob); the GPU side is rendered through the drop-in harness, which
+# generates the very same scene (tests/test_gpu_dropin.py).
+CASES_CRC = {
+    "synth10k_1080p_a4c": "-s synth -N 10000 -x 1920 -y 1080 -a 2",
+    "synth10k_8k_a4c":    "-s synth -N 10000 -x 7680 -y 4320 -a 2",
+    "synth100k_1080p_c":  "-s synth -N 100000 -x 1920 -y 1080",
+}
+
+
+def main_crc(names):
+    for name in names:
+        args = CASES_CRC[name].split()
+        with tempfile.TemporaryDirectory() as td:
+            rf = os.path.join(td, "r.raw")
+            jr = run([REF] + args + ["-t", str(os.cpu_count()), "-o", rf])
+            w, h = jr["x_res"], jr["y_res"]
+            frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
+        meta = {"name": name, "args": CASES_CRC[name], "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
+                "opts": jr["opts"], "ref_simd": jr["simd"], "ref_ms": jr["ms_min"], "ref_threads": jr["threads"],
+                "covered": float((frame != 0).mean())}
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, rowcrc=row_crcs(frame),
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print("%-20s %4dx%-4d ref %.0f ms  npz %7d B" % (name, w, h, jr["ms_min"], os.path.getsize(path)))
 
 
 def row_crcs(frame):
@@ -148,6 +179,7 @@ def main(names):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED))
+    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED) + list(CASES_CRC))
     main([n for n in names if n in CASES])
     main_hashed([n for n in names if n in CASES_HASHED])
+    main_crc([n for n in names if n in CASES_CRC])

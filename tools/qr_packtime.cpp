@@ -5,7 +5,7 @@
 int main(int argc,char**argv){
   FILE*f=fopen(argv[1],"rb"); fseek(f,0,SEEK_END); long n=ftell(f); fseek(f,0,SEEK_SET);
   void*b=malloc(n); if (fread(b,1,n,f) != (size_t)n) return 1; fclose(f);
-  qr_kpacker pk; void*out=aligned_alloc(64,4<<20);
+  qr_kpacker pk; void*out=aligned_alloc(64,(size_t)1<<30);
   for(int r=0;r<5;r++){
     auto t0=std::chrono::steady_clock::now();
     int rc=pk.plan(b);
