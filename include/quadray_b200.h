@@ -103,6 +103,29 @@ int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y
  */
 int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, int tile_row_step);
 
+/*
+ * Pipelined frames: the engine's update phases of frame N + 1 (rt_Scene::render
+ * phases 0.5-3 and the tiling merge, core/engine/engine.cpp:2976-3276 -- all
+ * host work) run while the GPUs render frame N, which the reference's
+ * update-barrier-render loop (root/RooT_linux.cpp:775-792) cannot do.
+ *
+ *   qr_pipeline(ctx, 1)        scenes alternate between two device slots, so
+ *                              qr_scene_upload does not wait for the frame in
+ *                              flight (only for the one begun two uploads ago)
+ *   qr_render_begin(ctx, &t)   queue the frame of the scene uploaded last into
+ *                              a page-locked frame owned by the library;
+ *                              returns at once with a ticket (0 or 1)
+ *   qr_render_end(ctx, t, frame, stride)
+ *                              wait for that frame, copy it to "frame"
+ *                              (geometry of the scene it was begun with;
+ *                              frame == NULL: wait and drop)
+ * At most two frames are in flight.  qr_pipeline(ctx, 0) drains and returns to
+ * the synchronous protocol (upload, qr_render).
+ */
+int qr_pipeline(qr_ctx *ctx, int on);
+int qr_render_begin(qr_ctx *ctx, int *ticket);
+int qr_render_end(qr_ctx *ctx, int ticket, uint32_t *frame, int stride);
+
 /* Wait for all queued work of the context. */
 int qr_sync(qr_ctx *ctx);
 

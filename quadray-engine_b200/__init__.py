@@ -26,7 +26,7 @@ SYMBOLS = (
     "qr_render_device", "qr_render_rows", "qr_sync", "qr_frame_device",
     "qr_frame_ipc_export", "qr_frame_ipc_open", "qr_frame_ipc_close", "qr_dump_hits",
     "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
-    "qr_kernel_query", "qr_fp32_peak",
+    "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_end",
 )
 
 
@@ -77,6 +77,12 @@ def load_library():
     lib.qr_frame_ipc_close.argtypes = [vp, vp]
     lib.qr_frame_ipc_close.restype = ci
     lib.qr_sync.argtypes = [vp]
+    lib.qr_pipeline.argtypes = [vp, ci]
+    lib.qr_pipeline.restype = ci
+    lib.qr_render_begin.argtypes = [vp, ctypes.POINTER(ci)]
+    lib.qr_render_begin.restype = ci
+    lib.qr_render_end.argtypes = [vp, ci, vp, ci]
+    lib.qr_render_end.restype = ci
     lib.qr_sync.restype = ci
     lib.qr_frame_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ci)]
     lib.qr_frame_device.restype = ci
@@ -164,6 +170,23 @@ class Context(object):
         if stride is None:
             stride = frame.strides[0] // 4 if frame.ndim == 2 else self.header["x_res"]
         self._check(self.lib.qr_render(self.h, _ptr(frame), int(stride)))
+        return frame
+
+    def pipeline(self, on=True):
+        """Pipelined frames: upload alternates between two scene slots,
+        render_begin queues a frame, render_end collects it."""
+        self._check(self.lib.qr_pipeline(self.h, 1 if on else 0))
+
+    def render_begin(self):
+        t = ctypes.c_int(-1)
+        self._check(self.lib.qr_render_begin(self.h, ctypes.byref(t)))
+        return (t.value, dict(self.header))
+
+    def render_end(self, ticket, frame=None):
+        t, h = ticket
+        if frame is None:
+            frame = np.zeros((h["y_res"], h["x_res"]), dtype=np.uint32)
+        self._check(self.lib.qr_render_end(self.h, t, _ptr(frame), frame.strides[0] // 4))
         return frame
 
     def render_frame(self):

@@ -349,8 +349,12 @@ struct qr_dev
     cudaStream_t    copy;                           /* D2H of finished chunks (GPU 0) */
     cudaEvent_t     ev0, ev1, done;
     cudaEvent_t     chunk_ev[QR_MAX_CHUNKS], copy_ev[QR_MAX_CHUNKS];
-    uint8_t        *blob_d;     size_t blob_cap;
-    uint8_t        *blob_h;     size_t blob_hcap;   /* pinned staging (dev 0 only) */
+    /* scene image: two slots, so that in pipelined mode the scene of frame
+     * N + 1 is packed and copied while the kernels of frame N still read theirs */
+    uint8_t        *blob_d[2];  size_t blob_cap[2];
+    uint8_t        *blob_h[2];  size_t blob_hcap[2];    /* pinned staging (dev 0 only) */
+    uint32_t       *frame_p[2]; size_t frame_pcap[2];   /* pinned frames of pipelined mode (dev 0 only) */
+    cudaEvent_t     pipe_ev[2];                         /* frame of slot k complete (dev 0 only) */
     uint32_t       *frame_d;    size_t frame_cap;   /* bytes */
     uint32_t       *frame_h;    size_t frame_hcap;  /* pinned (dev 0 only) */
     float          *t_d;        size_t t_cap;
@@ -377,6 +381,10 @@ struct qr_ctx
     int             pin_frames;     /* QR_B200_PIN_FRAME=1: page-lock the caller's framebuffer on first use */
     int             zerocopy;       /* store pixels straight into a page-locked host frame (QR_B200_ZEROCOPY=0: off) */
     void           *pinned[4];      /* framebuffers registered that way */
+    int             pipelined;      /* qr_pipeline(ctx, 1): scenes alternate between two slots */
+    int             slot;           /* slot of the current scene */
+    bool            pending[2];     /* a frame begun in this slot has not been collected */
+    qr_blob_header  pend_hdr[2];    /* its geometry */
     cudaFuncAttributes fattr;
     qr_kpacker      packer;
     char            err[512];
@@ -564,8 +572,13 @@ extern "C" void qr_shutdown(qr_ctx *ctx)
         if (d.ev0)     cudaEventDestroy(d.ev0);
         if (d.ev1)     cudaEventDestroy(d.ev1);
         if (d.done)    cudaEventDestroy(d.done);
-        if (d.blob_d)  cudaFree(d.blob_d);
-        if (d.blob_h)  cudaFreeHost(d.blob_h);
+        for (int k = 0; k < 2; k++)
+        {
+            if (d.blob_d[k])  cudaFree(d.blob_d[k]);
+            if (d.blob_h[k])  cudaFreeHost(d.blob_h[k]);
+            if (d.frame_p[k]) cudaFreeHost(d.frame_p[k]);
+            if (d.pipe_ev[k]) cudaEventDestroy(d.pipe_ev[k]);
+        }
         if (d.frame_d) cudaFree(d.frame_d);
         if (d.frame_h) cudaFreeHost(d.frame_h);
         if (d.t_d)     cudaFree(d.t_d);
@@ -660,29 +673,44 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
 
     qr_dev &d0 = ctx->dev[0];
     QR_CUDA(ctx, cudaSetDevice(d0.id));
-    /* the previous frame's H2D copies read the staging buffer */
-    for (int i = 0; i < ctx->ndev; i++)
+    if (ctx->pipelined)
     {
-        QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+        /* the other slot: free once the frame begun in it two uploads ago is
+         * complete (its kernels read the slot's device image, and the H2D
+         * copies of the pinned staging precede them on the same streams) */
+        ctx->slot ^= 1;
+        if (d0.pipe_ev[ctx->slot] != NULL)
+        {
+            QR_CUDA(ctx, cudaEventSynchronize(d0.pipe_ev[ctx->slot]));
+        }
     }
-    rc = qr_grow(ctx, (void **)&d0.blob_h, &d0.blob_hcap, n, true);
+    else
+    {
+        /* the previous frame's H2D copies read the staging buffer */
+        for (int i = 0; i < ctx->ndev; i++)
+        {
+            QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+        }
+    }
+    const int sl = ctx->slot;
+    rc = qr_grow(ctx, (void **)&d0.blob_h[sl], &d0.blob_hcap[sl], n, true);
     if (rc != QR_OK)
     {
         return rc;
     }
-    pk.write(d0.blob_h);
-    const qr_blob_header *kh = (const qr_blob_header *)d0.blob_h;
+    pk.write(d0.blob_h[sl]);
+    const qr_blob_header *kh = (const qr_blob_header *)d0.blob_h[sl];
 
     for (int i = 0; i < ctx->ndev; i++)
     {
         qr_dev &d = ctx->dev[i];
         QR_CUDA(ctx, cudaSetDevice(d.id));
-        rc = qr_grow(ctx, (void **)&d.blob_d, &d.blob_cap, n, false);
+        rc = qr_grow(ctx, (void **)&d.blob_d[sl], &d.blob_cap[sl], n, false);
         if (rc != QR_OK)
         {
             return rc;
         }
-        QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d, d0.blob_h, n, cudaMemcpyHostToDevice, d.stream));
+        QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d[sl], d0.blob_h[sl], n, cudaMemcpyHostToDevice, d.stream));
     }
 
     ctx->hdr = *h;
@@ -736,7 +764,7 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     }
 
     qr_launch p;
-    p.blob = d.blob_d;
+    p.blob = d.blob_d[ctx->slot];
     p.frame = frame_dev;
     p.stride = stride;
     p.ty0 = ty0;
@@ -1069,6 +1097,143 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
             for (int y = ya; y < yb; y++)
             {
                 memcpy(frame + (ptrdiff_t)y * stride, d0.frame_h + (size_t)y * dstride, wbytes);
+            }
+        }
+    }
+    return QR_OK;
+}
+
+/*
+ * Pipelined frames (the host's update phases of frame
+ * N + 1 run while the GPUs render frame N).  qr_render_begin queues the frame
+ * of the scene uploaded last into an internal page-locked frame of its slot
+ * and returns at once; qr_render_end waits for that frame and copies it out.
+ * Two frames can be in flight; qr_scene_upload alternates the scene slot.
+ */
+extern "C" int qr_pipeline(qr_ctx *ctx, int on)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    int rc = qr_sync(ctx);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    for (int k = 0; k < 2; k++)
+    {
+        ctx->pending[k] = false;
+        if (on && d0.pipe_ev[k] == NULL)
+        {
+            QR_CUDA(ctx, cudaEventCreateWithFlags(&d0.pipe_ev[k], cudaEventDisableTiming));
+        }
+    }
+    if ((on != 0) != (ctx->pipelined != 0))
+    {
+        /* the current scene lives in the slot it was uploaded to; after a mode
+         * change the next upload decides */
+        ctx->have_scene = false;
+        ctx->slot = 0;
+    }
+    ctx->pipelined = on != 0;
+    return QR_OK;
+}
+
+extern "C" int qr_render_begin(qr_ctx *ctx, int *ticket)
+{
+    if (ctx == NULL || ticket == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->pipelined || !ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_begin: needs qr_pipeline(ctx, 1) and an uploaded scene");
+    }
+    const int sl = ctx->slot;
+    if (ctx->pending[sl])
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_begin: the frame begun in this slot was not collected");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    const int dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+    const size_t fbytes = (size_t)dstride * h.y_res * sizeof(uint32_t);
+    qr_dev &d0 = ctx->dev[0];
+    int rc;
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    rc = qr_grow(ctx, (void **)&d0.frame_p[sl], &d0.frame_pcap[sl], fbytes, true);
+    if (rc != QR_OK)
+    {
+        return rc;
+    }
+
+    bool done = false;
+    if (ctx->ndev == 1 && ctx->zerocopy)
+    {
+        /* the kernel stores its pixels straight into the page-locked frame */
+        uint32_t *dev_view = NULL;
+        if (cudaHostGetDevicePointer((void **)&dev_view, d0.frame_p[sl], 0) == cudaSuccess && dev_view != NULL)
+        {
+            rc = qr_launch_rows(ctx, 0, dev_view, dstride, 0, 1, h.tls_col, NULL);
+            if (rc != QR_OK)
+            {
+                return rc;
+            }
+            done = true;
+        }
+        cudaGetLastError();
+    }
+    if (!done)
+    {
+        rc = qr_render_all(ctx, NULL);
+        if (rc != QR_OK)
+        {
+            return rc;
+        }
+        QR_CUDA(ctx, cudaSetDevice(d0.id));
+        QR_CUDA(ctx, cudaMemcpyAsync(d0.frame_p[sl], d0.frame_d, fbytes, cudaMemcpyDeviceToHost, d0.stream));
+    }
+    QR_CUDA(ctx, cudaEventRecord(d0.pipe_ev[sl], d0.stream));
+    ctx->pending[sl] = true;
+    ctx->pend_hdr[sl] = h;
+    *ticket = sl;
+    return QR_OK;
+}
+
+extern "C" int qr_render_end(qr_ctx *ctx, int ticket, uint32_t *frame, int stride)
+{
+    if (ctx == NULL || ticket < 0 || ticket > 1)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->pending[ticket])
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_end: no frame in flight for this ticket");
+    }
+    const qr_blob_header &h = ctx->pend_hdr[ticket];
+    if (frame != NULL && (stride < h.x_res && -stride < h.x_res))
+    {
+        return qr_fail(ctx, QR_E_ARG, "qr_render_end: stride smaller than x_res");
+    }
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    QR_CUDA(ctx, cudaEventSynchronize(d0.pipe_ev[ticket]));
+    ctx->pending[ticket] = false;
+    if (frame != NULL)
+    {
+        const int dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+        const size_t wbytes = (size_t)h.x_res * sizeof(uint32_t);
+        if (stride == dstride && stride == h.x_res)
+        {
+            memcpy(frame, d0.frame_p[ticket], wbytes * h.y_res);
+        }
+        else
+        {
+            for (int y = 0; y < h.y_res; y++)
+            {
+                memcpy(frame + (ptrdiff_t)y * stride, d0.frame_p[ticket] + (size_t)y * dstride, wbytes);
             }
         }
     }

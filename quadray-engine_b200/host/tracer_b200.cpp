@@ -85,6 +85,16 @@ rt_si32 rt_Platform::switch0(rt_SIMD_INFOX *s_inf, rt_si32 simd)
 static qr_ctx      *g_ctx = RT_NULL;
 static qr_Flattener g_flat;
 static char         g_err[600];
+static bool         g_pipelined = false;
+
+/* pipelined mode: the frame in flight and the buffer it belongs to */
+static struct
+{
+    int      ticket;
+    rt_pntr  frame;
+    rt_si32  row, w, h;
+}
+g_prev = { -1, RT_NULL, 0, 0, 0 };
 
 static double qr_now_ms()
 {
@@ -143,6 +153,16 @@ static rt_void qr_context()
         qr_throw("B200 backend init failed", RT_NULL);
     }
     atexit(qr_atexit);
+
+    const char *pipe = getenv("QR_B200_PIPELINE");
+    if (pipe != RT_NULL && pipe[0] == '1')
+    {
+        if (qr_pipeline(g_ctx, 1) != QR_OK)
+        {
+            qr_throw("B200 pipelined mode failed", g_ctx);
+        }
+        g_pipelined = true;
+    }
 }
 
 /*
@@ -175,6 +195,47 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
         qr_throw("B200 scene upload failed", g_ctx);
     }
     const double t2 = timing ? qr_now_ms() : 0.0;
+    if (g_pipelined)
+    {
+        /*
+         * QR_B200_PIPELINE=1: this call queues frame N and hands back frame
+         * N - 1, so the engine's update phases of the next frame overlap the
+         * GPU.  The very first frame (and the first after a change of frame
+         * buffer or geometry) is rendered synchronously, the call after it
+         * leaves the caller's buffer as it is: the caller sees F0 F0 F1 F2 ...
+         */
+        int ticket = -1;
+        if (qr_render_begin(g_ctx, &ticket) != QR_OK)
+        {
+            qr_throw("B200 render failed", g_ctx);
+        }
+        const bool same = g_prev.frame == s_inf->frame && g_prev.row == s_inf->frm_row
+                       && g_prev.w == s_inf->frm_w && g_prev.h == s_inf->frm_h;
+        int rc = QR_OK;
+        if (g_prev.ticket >= 0)
+        {
+            rc = same ? qr_render_end(g_ctx, g_prev.ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row)
+                      : qr_render_end(g_ctx, g_prev.ticket, RT_NULL, 0);
+            g_prev.ticket = -1;
+        }
+        if (rc == QR_OK && !same)
+        {
+            /* nothing older belongs in this buffer: wait for this very frame */
+            rc = qr_render_end(g_ctx, ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row);
+        }
+        else
+        if (rc == QR_OK)
+        {
+            g_prev.ticket = ticket;
+        }
+        if (rc != QR_OK)
+        {
+            qr_throw("B200 render failed", g_ctx);
+        }
+        g_prev.frame = s_inf->frame; g_prev.row = s_inf->frm_row;
+        g_prev.w = s_inf->frm_w;     g_prev.h = s_inf->frm_h;
+    }
+    else
     if (qr_render(g_ctx, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
     {
         qr_throw("B200 render failed", g_ctx);

@@ -24,10 +24,12 @@ HARNESS = os.path.join(ROOT, "build", "qr_b200_harness")
 CORE_TEST = os.path.join(ROOT, "build", "core_test_b200")
 
 
-def run_harness(args, tmp_path):
+def run_harness(args, tmp_path, env=None):
     out = str(tmp_path / "frame.raw")
+    e = dict(os.environ)
+    e.update(env or {})
     p = subprocess.run([HARNESS] + args + ["-o", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                       timeout=600)
+                       timeout=600, env=e)
     assert p.returncode == 0, p.stderr.decode()
     info = json.loads(p.stdout.decode().strip().splitlines()[-1])
     frame = np.fromfile(out, dtype=np.uint32).reshape(info["y_res"], info["x_res"])
@@ -72,6 +74,24 @@ def test_scene_api_animation_and_update_phases(tmp_path):
     b, _ = run_harness(["-s", "demo01", "-a", "2", "-f", "3", "-b", "0", "-d", "500"], tmp_path)
     assert a.shape == b.shape and a.any() and b.any()
     assert int((a != b).sum()) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
+def test_scene_api_pipelined_mode_lags_one_frame(tmp_path):
+    """QR_B200_PIPELINE=1 (update of frame N + 1 overlaps the GPU's frame N):
+    the caller sees F0 F0 F1 F2 ..., every frame identical to the synchronous
+    run's; host threads run the update phases (-t 4)."""
+    args = ["-s", "demo01", "-a", "2", "-b", "0", "-d", "500", "-t", "4"]
+    sync3, _ = run_harness(args + ["-f", "3"], tmp_path)                     # F2
+    sync4, _ = run_harness(args + ["-f", "4"], tmp_path)                     # F3
+    pipe4, _ = run_harness(args + ["-f", "4"], tmp_path, {"QR_B200_PIPELINE": "1"})
+    pipe5, _ = run_harness(args + ["-f", "5"], tmp_path, {"QR_B200_PIPELINE": "1"})
+    assert int((sync3 != sync4).sum()) > 0
+    assert np.array_equal(pipe4, sync3)
+    assert np.array_equal(pipe5, sync4)
+    one, _ = run_harness(args + ["-f", "1"], tmp_path, {"QR_B200_PIPELINE": "1"})
+    first, _ = run_harness(args + ["-f", "1"], tmp_path)
+    assert np.array_equal(one, first)                                         # the first frame is synchronous
 
 
 @pytest.mark.skipif(not os.path.exists(CORE_TEST), reason="build/core_test_b200 was not built")

@@ -251,3 +251,43 @@ def test_gpu_multi_device_context(entry, pkg):
             assert counts["primary"] == ref.size << 2
         finally:
             c.close()
+
+
+def test_gpu_pipelined_frames(entry, pkg):
+    """qr_pipeline / qr_render_begin / qr_render_end: two frames of different
+    scenes and geometries in flight, each collected frame is the reference's;
+    the scene of the second is uploaded while the first renders."""
+    c = pkg.Context([0])
+    try:
+        c.pipeline(True)
+        names = ["demo03_a4g", "test05_odd", "test17_full_a4", "demo02_a4g", "test12_full"]
+        refs, tickets = {}, []
+        for i, name in enumerate(names):
+            blob, ref, _ = entry.load_golden(name)
+            refs[name] = ref
+            c.upload(blob)
+            tickets.append((name, c.render_begin()))
+            if len(tickets) == 2:
+                n0, t0 = tickets.pop(0)
+                got = c.render_end(t0)
+                assert np.array_equal(got, refs[n0]), n0
+        n0, t0 = tickets.pop(0)
+        assert np.array_equal(c.render_end(t0), refs[n0]), n0
+        # a third frame in flight is refused, a ticket cannot be collected twice
+        blob, ref, _ = entry.load_golden("test01_full")
+        c.upload(blob); ta = c.render_begin()
+        c.upload(blob); tb = c.render_begin()
+        c.upload(blob)
+        with pytest.raises(pkg.QuadRayError) as ei:
+            c.render_begin()
+        assert ei.value.code == pkg.QR_E_STATE
+        assert np.array_equal(c.render_end(ta), ref)
+        with pytest.raises(pkg.QuadRayError):
+            c.render_end(ta)
+        assert np.array_equal(c.render_end(tb), ref)
+        # back to the synchronous protocol
+        c.pipeline(False)
+        c.upload(blob)
+        assert np.array_equal(c.render_frame(), ref)
+    finally:
+        c.close()
