@@ -13,6 +13,7 @@
  */
 
 #include <stdio.h>
+#include <sys/time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -66,6 +67,22 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
 
     size_t bytes = 0;
     const uint8_t *blob = g_flat.build(s_inf, &bytes);
+
+    /* QR_FLATTEN_REPEAT=n: time n more flattener passes of this frame (the
+     * product's host-side cost, measurable without a GPU) */
+    const char *rep = getenv("QR_FLATTEN_REPEAT");
+    if (rep != NULL && atoi(rep) > 0)
+    {
+        timeval a, b;
+        gettimeofday(&a, NULL);
+        for (int i = 0; i < atoi(rep); i++)
+        {
+            blob = g_flat.build(s_inf, &bytes);
+        }
+        gettimeofday(&b, NULL);
+        fprintf(stderr, "flatten: %.3f ms per pass (%zu bytes)\n",
+                ((b.tv_sec - a.tv_sec) * 1e3 + (b.tv_usec - a.tv_usec) / 1e3) / atoi(rep), bytes);
+    }
 
     const char *dump = getenv("QR_DUMP_BLOB");
     if (dump != NULL && dump[0] != 0)
