@@ -162,6 +162,10 @@ template <> struct qr_hot<true>
  *         it meets the surface the ray left
  *   COL RAY NRM TEX   shading state of a level while its shadow ray is walked
  *   MISC  primary T_BUF and the ray counters (shadow, reflection, refraction)
+ *   WORG WRAY  the ray in world space while the walk works on a copy that it
+ *         transforms in place (open transform node / surface with a matrix);
+ *         read back when a node closes, by the clipper for the world hit
+ *         point inside a node, and by the shader after the walk
  * Quad q of thread t sits at base + q * stride + t * 16: a warp's 128-bit
  * access covers 512 contiguous bytes (no bank conflicts).
  */
@@ -172,7 +176,9 @@ template <> struct qr_hot<true>
 #define QR_SC_NRM    4
 #define QR_SC_TEX    5
 #define QR_SC_MISC   6
-#define QR_SC_QUADS  7
+#define QR_SC_WORG   7      /* world origin / direction of the ray being walked: parked for */
+#define QR_SC_WRAY   8      /* the walk, which transforms its copy in place inside nodes */
+#define QR_SC_QUADS  9
 
 #if defined(__CUDACC__)
 /* (the host pass of nvcc parses these too; it never calls them) */
@@ -521,11 +527,20 @@ QR_HD_COLD bool qr_clip_custom(const typename qr_hot<SH>::base_t surf, const qr_
  */
 template <bool SH>
 QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0,
-                   float ox, float oy, float oz, float rx, float ry, float rz,
+                   const qr_scratch sc, bool xf, float bo0, float bo1, float bo2,
                    float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
                    float t, bool dmask, uint32_t amask, int side,
                    float &lx, float &ly, float &lz)
 {
+    /* the world ray: the current frame itself, or parked in the scratch while
+     * the walk is inside a transform node / a surface's own matrix */
+    float ox = bo0, oy = bo1, oz = bo2, rx = lr0, ry = lr1, rz = lr2;
+    if (xf)
+    {
+        const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
+        ox = wo.x; oy = wo.y; oz = wo.z;
+        rx = wr.x; ry = wr.y; rz = wr.z;
+    }
     const float hx = qr_add(qr_mul(rx, t), ox);
     const float hy = qr_add(qr_mul(ry, t), oy);
     const float hz = qr_add(qr_mul(rz, t), oz);
@@ -607,8 +622,13 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                    float t_min, float t_max, uint32_t p_obj, int p_flg,
                    const qr_scratch sc, float &t_buf)
 {
+    /* (bo, cr): origin and direction in the current frame, transformed IN
+     * PLACE; the world ray waits in the scratch (xf: current frame != world) */
+    qr_sc_st(sc, QR_SC_WORG, ox, oy, oz, 0.0f);
+    qr_sc_st(sc, QR_SC_WRAY, rx, ry, rz, 0.0f);
     float bo0 = ox, bo1 = oy, bo2 = oz;
     float cr0 = rx, cr1 = ry, cr2 = rz;
+    bool  xf = false;
     const int  pf = p_flg & (QR_FLAG_SIDE | QR_FLAG_PASS);
     /* a root t <= 0 (or NaN) can never pass t_min < t when t_min >= 0 */
     const bool no_neg = !(t_min < 0.0f);
@@ -645,9 +665,18 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 const qr_f4 q5 = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
                 const float tckz = QR_SURF(v, so, 7).x;
                 const uint32_t trm = QR_D_TRM(qr_f2u(q0.w));
-                qr_xform(q5, q6, tckz, trm, qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                if (xf)
+                {
+                    /* nodes do not nest (the element compiler closes one before
+                     * it opens the next); should one ever, start from the world */
+                    const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
+                    bo0 = wo.x; bo1 = wo.y; bo2 = wo.z;
+                    cr0 = wr.x; cr1 = wr.y; cr2 = wr.z;
+                }
+                qr_xform(q5, q6, tckz, trm, qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
                          bo0, bo1, bo2);
-                qr_xform(q5, q6, tckz, trm, rx, ry, rz, cr0, cr1, cr2);
+                qr_xform(q5, q6, tckz, trm, cr0, cr1, cr2, cr0, cr1, cr2);
+                xf = true;
             }
             ei = ni;
             e = en;
@@ -713,12 +742,13 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 /* OO_dff 1429-1556: surface with its own matrix */
                 const qr_f4 q5t = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
                 const float tckz = QR_SURF(v, so, 7).x;
-                qr_xform(q5t, q6, tckz, QR_D_TRM(d), rx, ry, rz, cr0, cr1, cr2);
                 if (!same)
                 {
-                    qr_xform(q5t, q6, tckz, QR_D_TRM(d), qr_sub(ox, q0.x), qr_sub(oy, q0.y), qr_sub(oz, q0.z),
+                    qr_xform(q5t, q6, tckz, QR_D_TRM(d), qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
                              ld0, ld1, ld2);
                 }
+                qr_xform(q5t, q6, tckz, QR_D_TRM(d), cr0, cr1, cr2, cr0, cr1, cr2);
+                xf = true;
             }
             else
             {
@@ -876,7 +906,7 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 if (!qr_gt(t_buf, t)) continue;
                 if (!(t_min < t)) continue;
                 float lx, ly, lz;
-                if (!qr_clip<SH>(v, so, d, q0, ox, oy, oz, rx, ry, rz, cr0, cr1, cr2, ld0, ld1, ld2,
+                if (!qr_clip<SH>(v, so, d, q0, sc, xf, bo0, bo1, bo2, cr0, cr1, cr2, ld0, ld1, ld2,
                                  t, dmask, amask, side, lx, ly, lz)) continue;
                 if (mode == QR_MODE_SHADOW)
                 {
@@ -892,9 +922,14 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
         while (0);
 
         /* after the last element of the open transform node / an own matrix:
-         * back to the world (predicated moves) */
-        bo0 = reset ? ox : bo0; bo1 = reset ? oy : bo1; bo2 = reset ? oz : bo2;
-        cr0 = reset ? rx : cr0; cr1 = reset ? ry : cr1; cr2 = reset ? rz : cr2;
+         * back to the world */
+        if (reset)
+        {
+            const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
+            bo0 = wo.x; bo1 = wo.y; bo2 = wo.z;
+            cr0 = wr.x; cr1 = wr.y; cr2 = wr.z;
+            xf = false;
+        }
         ei = ni;
         e = en;
     }
@@ -1040,6 +1075,13 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         float t_buf;
         const bool res = qr_walk<SH>(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
                                      p_obj, p_flg, sc, t_buf);
+        {
+            /* the ray comes back from where the walk parked it, so it does not
+             * occupy registers during the walk */
+            const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
+            ox = wo.x; oy = wo.y; oz = wo.z;
+            rx = wr.x; ry = wr.y; rz = wr.z;
+        }
         int resume = 0;                 /* 0 none, 1 after refraction, 2 after reflection, -1 return */
 
         if (mode == QR_MODE_SHADOW)
