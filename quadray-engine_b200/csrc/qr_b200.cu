@@ -42,6 +42,8 @@ static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {38
                                      {896, 1}, {1024, 1} };
 #define QR_N_SHAPES     8
 #define QR_DEFAULT_SHAPE 2
+#define QR_BIG_SHAPE     7          /* 1024 threads at 64 registers */
+#define QR_BIG_FRAME_ITEMS 150000   /* work items (32 samples each) per GPU from which QR_BIG_SHAPE pays */
 
 /* ------------------------------------------------------------------ PTX --- */
 
@@ -377,6 +379,7 @@ struct qr_ctx
     uint64_t        launches;
     uint64_t        rays[4];
     int             shape;          /* index into g_shapes */
+    int             shape_fixed;    /* QR_B200_SHAPE given: no automatic choice per frame size */
     int             chunks;         /* qr_render(host frame) pipeline depth on one GPU, 0 = automatic */
     int             pin_frames;     /* QR_B200_PIN_FRAME=1: page-lock the caller's framebuffer on first use */
     int             zerocopy;       /* store pixels straight into a page-locked host frame (QR_B200_ZEROCOPY=0: off) */
@@ -532,6 +535,7 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         if (env != NULL && env[0] >= '0' && env[0] < '0' + QR_N_SHAPES && env[1] == 0)
         {
             ctx->shape = env[0] - '0';
+            ctx->shape_fixed = 1;
         }
     }
     cudaSetDevice(ctx->dev[0].id);
@@ -715,6 +719,27 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
 
     ctx->hdr = *h;
     ctx->have_scene = true;
+
+    /*
+     * Launch shape by the amount of work of a full-frame launch.  The walk is
+     * latency-bound (dependent FP chains, list elements through L1/L2), so the
+     * big frames want every warp slot of the SM even at 64 registers with a
+     * few spills (1080p 4xAA, RooT default scene: 1.90 ms at 1024 threads,
+     * 2.07 ms at 640); with few work items per warp the smaller CTA's cleaner
+     * code and finer tail win (800 x 480: 0.18 vs 0.22 ms on demo01).
+     */
+    if (!ctx->shape_fixed)
+    {
+        const int bh = 8 >> h->fsaa;
+        const uint64_t items = (uint64_t)h->tls_col * h->tls_row
+                             * (uint64_t)((h->tile_h + bh - 1) / bh) * (uint64_t)((h->tile_w + 3) / 4);
+        const int want = items >= (uint64_t)QR_BIG_FRAME_ITEMS * ctx->ndev ? QR_BIG_SHAPE : QR_DEFAULT_SHAPE;
+        if (want != ctx->shape)
+        {
+            ctx->shape = want;
+            QR_CUDA(ctx, cudaFuncGetAttributes(&ctx->fattr, (const void *)qr_kernel_of(true, ctx->shape)));
+        }
+    }
 
     /* shared-memory staging of the kscene prefix */
     const uint32_t prefix = kh->off_elem;

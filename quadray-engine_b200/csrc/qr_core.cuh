@@ -161,6 +161,9 @@ template <> struct qr_hot<true>
  *         previous context, tracer.cpp:1352-1373): read by the walk only when
  *         it meets the surface the ray left
  *   COL RAY NRM TEX   shading state of a level while its shadow ray is walked
+ *         (COL shares its quad with BEST: the best-hit record is consumed by
+ *         the shader before it parks anything, and shadow walks write no
+ *         BEST)
  *   MISC  primary T_BUF and the ray counters (shadow, reflection, refraction)
  *   WORG WRAY  the ray in world space while the walk works on a copy that it
  *         transforms in place (open transform node / surface with a matrix);
@@ -169,16 +172,16 @@ template <> struct qr_hot<true>
  * Quad q of thread t sits at base + q * stride + t * 16: a warp's 128-bit
  * access covers 512 contiguous bytes (no bank conflicts).
  */
-#define QR_SC_BEST   0
+#define QR_SC_BEST   0      /* closest-hit walks only ...                                   */
+#define QR_SC_COL    0      /* ... shadow walks only: the two never hold live data together */
 #define QR_SC_LOC    1
-#define QR_SC_COL    2
-#define QR_SC_RAY    3
-#define QR_SC_NRM    4
-#define QR_SC_TEX    5
-#define QR_SC_MISC   6
-#define QR_SC_WORG   7      /* world origin / direction of the ray being walked: parked for */
-#define QR_SC_WRAY   8      /* the walk, which transforms its copy in place inside nodes */
-#define QR_SC_QUADS  9
+#define QR_SC_RAY    2
+#define QR_SC_NRM    3
+#define QR_SC_TEX    4
+#define QR_SC_MISC   5
+#define QR_SC_WORG   6      /* world origin / direction of the ray being walked: parked for */
+#define QR_SC_WRAY   7      /* the walk, which transforms its copy in place inside nodes */
+#define QR_SC_QUADS  8
 
 #if defined(__CUDACC__)
 /* (the host pass of nvcc parses these too; it never calls them) */

@@ -212,12 +212,46 @@ class qr_kpacker
             out[fix[i].at].aux = n;
         }
 
+        /* materials are deduplicated by content: the engine keeps one record
+         * per surface side, most of them copies (RooT's default scene: 346
+         * records, a few dozen distinct), and the material table is part of
+         * the prefix a CTA stages in shared memory */
+        {
+            const qr_material *mt = (const qr_material *)(blob + h->off_mat);
+            mat_map.assign((size_t)h->n_mat, 0);
+            mat_uniq.clear();
+            mat_bucket.clear();
+            for (int i = 0; i < h->n_mat; i++)
+            {
+                uint64_t hv = 1469598103934665603ull;
+                const uint32_t *w = (const uint32_t *)&mt[i];
+                for (size_t j = 0; j < sizeof(qr_material) / 4; j++)
+                {
+                    hv = (hv ^ w[j]) * 1099511628211ull;
+                }
+                std::vector<int32_t> &b = mat_bucket[hv];
+                int32_t u = -1;
+                for (size_t j = 0; j < b.size() && u < 0; j++)
+                {
+                    if (memcmp(&mt[mat_uniq[(size_t)b[j]]], &mt[i], sizeof(qr_material)) == 0) u = b[j];
+                }
+                if (u < 0)
+                {
+                    u = (int32_t)mat_uniq.size();
+                    mat_uniq.push_back(i);
+                    b.push_back(u);
+                }
+                mat_map[(size_t)i] = u;
+            }
+        }
+
         k = *h;
         uint32_t off = sizeof(qr_blob_header);
         k.flags = QR_KSCENE_FLAG;
+        k.n_mat = (int32_t)mat_uniq.size();
         k.off_surf = off;   off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSURF_QUADS * 16);
         k.pad3[0] = (int32_t)off; off = qr_k_align16(off + (uint32_t)h->n_surf * QR_KSHADE_QUADS * 16);
-        k.off_mat = off;    off = qr_k_align16(off + (uint32_t)h->n_mat * QR_KMAT_QUADS * 16);
+        k.off_mat = off;    off = qr_k_align16(off + (uint32_t)mat_uniq.size() * QR_KMAT_QUADS * 16);
         k.off_lgt = off;    off = qr_k_align16(off + (uint32_t)h->n_lgt * QR_KLGT_QUADS * 16);
         k.off_elem = off;   off = qr_k_align16(off + (uint32_t)out.size() * (uint32_t)sizeof(qr_kelem));
         k.n_elem = (int32_t)out.size();
@@ -281,17 +315,17 @@ class qr_kpacker
             q[7].x = s.tck[2]; q[7].y = s.d_eps;  q[7].z = s.t_eps;  q[7].w = qr_k_bits(s.c_def);
 
             qr_f4 *g = kh + (size_t)i * QR_KSHADE_QUADS;
-            g[0].x = qr_k_bits((uint32_t)s.mat[0]);         g[0].y = qr_k_bits((uint32_t)s.mat[1]);
+            g[0].x = qr_k_bits((uint32_t)kmat_of(s.mat[0])); g[0].y = qr_k_bits((uint32_t)kmat_of(s.mat[1]));
             g[0].z = qr_k_bits((uint32_t)k_lgt[2 * i]);     g[0].w = qr_k_bits((uint32_t)k_lgt[2 * i + 1]);
             g[1].x = qr_k_bits((uint32_t)k_srf[2 * i]);     g[1].y = qr_k_bits((uint32_t)k_srf[2 * i + 1]);
             g[1].z = 0.0f; g[1].w = 0.0f;
         }
 
         qr_f4 *km = (qr_f4 *)(o + k.off_mat);
-        for (int i = 0; i < h->n_mat; i++)
+        for (size_t i = 0; i < mat_uniq.size(); i++)
         {
-            const qr_material &m = mt[i];
-            qr_f4 *q = km + (size_t)i * QR_KMAT_QUADS;
+            const qr_material &m = mt[mat_uniq[i]];
+            qr_f4 *q = km + i * QR_KMAT_QUADS;
             const uint32_t ys = (m.yshft & 0xFFu) | ((uint32_t)(m.t_map[0] & 1) << 8) | ((uint32_t)(m.t_map[1] & 1) << 9);
             q[0].x = m.xscal; q[0].y = m.yscal; q[0].z = m.xoffs; q[0].w = m.yoffs;
             q[1].x = qr_k_bits(m.xmask); q[1].y = qr_k_bits(m.ymask); q[1].z = qr_k_bits(ys); q[1].w = qr_k_bits((uint32_t)m.tex);
@@ -318,6 +352,12 @@ class qr_kpacker
     private:
 
     static qr_kelem make(uint32_t w, int32_t aux) { qr_kelem e; e.w = w; e.aux = aux; return e; }
+
+    /* index of a blob material in the deduplicated table */
+    int32_t kmat_of(int32_t m) const
+    {
+        return m >= 0 && m < h->n_mat ? mat_map[(size_t)m] : m;
+    }
 
     /*
      * Surface list: compiled and emitted once; a tail shared with a list
@@ -475,6 +515,8 @@ class qr_kpacker
     struct qr_kfix { int32_t at, target, state; };      /* BV element, old skip target, state there */
     std::vector<uint8_t>  sinfo;
     std::vector<int32_t>  state, nidx, k_tiles, k_srf, k_lgt, k_clip, shadow;
+    std::vector<int32_t>  mat_map, mat_uniq;            /* blob material -> table index, table index -> blob material */
+    std::unordered_map<uint64_t, std::vector<int32_t> > mat_bucket;
     std::vector<qr_kelem> out;
     std::vector<qr_kfix>  fix;
     std::unordered_map<int32_t, int32_t> heads;
