@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libquadray_b200.so")
+# QR_B200_LIB: another build of the same library (kernel A/B runs: tools/tune_shapes.py)
+LIB_PATH = os.environ.get("QR_B200_LIB") or os.path.join(_HERE, "lib", "libquadray_b200.so")
 
 QR_OK, QR_E_ARG, QR_E_BLOB, QR_E_CUDA, QR_E_NODEV, QR_E_STATE = 0, -1, -2, -3, -4, -5
 
