@@ -164,6 +164,19 @@ def cpu_baseline(blob, meta, frames, warmup):
 
 # -------------------------------------------------------- reference arm ---
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The JSON line, on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main_reference(args, rank, world):
     if rank != 0:
         return 0
@@ -180,7 +193,7 @@ def main_reference(args, rank, world):
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -499,7 +512,7 @@ def main_gpu(args, rank, world, local_rank):
             line["roofline"] = roofline
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line))
+        emit(line)
 
     if remote_ptr is not None:
         ctx.frame_ipc_close(remote_ptr)
@@ -525,6 +538,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # stdout carries the ONE JSON line and nothing else: libraries that write to
+    # file descriptor 1 on their own (NCCL prints its version there) go to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if world == 1 and args.gpus > 1:
         sys.stderr.write("bench.py: --gpus %d without torchrun: running the single-process multi-GPU "
                          "context is not the benchmark contract; launch with torch.distributed.run\n" % args.gpus)
