@@ -439,10 +439,12 @@ def main_gpu(args, rank, world, local_rank):
         def run_pipe(n):
             prev = None
             for _ in range(n):
+                if prev is not None:
+                    ctx.render_fetch(prev, hf)          # D2H of the previous frame beside the pack + H2D
                 ctx.upload(blob_h)
                 tk = ctx.render_begin()
                 if prev is not None:
-                    ctx.render_end(prev, hf)
+                    ctx.render_end(prev, hf, fetched=True)
                 prev = tk
             ctx.render_end(prev, hf)
 
@@ -501,9 +503,9 @@ def main_gpu(args, rank, world, local_rank):
                 "value": rays * args.steps / e2e_pipe_s / 1e6, "unit": UNIT,
                 "ms_per_step": e2e_pipe_s / args.steps * 1e3,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "path": "per step: qr_scene_upload(host blob: pack + pinned H2D) + qr_render_begin + qr_render_end "
-                        "of the previous step into the host frame (two frames in flight; the kernel stores into a "
-                        "page-locked frame over PCIe)",
+                "path": "per step: qr_render_fetch(previous frame -> page-locked host frame, DMA) + "
+                        "qr_scene_upload(host blob: pack + pinned H2D) + qr_render_begin + qr_render_end(previous "
+                        "frame); two frames in flight",
                 "pixels_differ_vs_reference_cpu_frame": e2e_pipe_parity,
                 "synchronous": {"value": sync["value"], "ms_per_step": sync["ms_per_step"], "path": sync["path"],
                                 "pixels_differ_vs_reference_cpu_frame": sync["pixels_differ_vs_reference_cpu_frame"]},

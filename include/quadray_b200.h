@@ -115,15 +115,24 @@ int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, 
  *   qr_render_begin(ctx, &t)   queue the frame of the scene uploaded last into
  *                              a page-locked frame owned by the library;
  *                              returns at once with a ticket (0 or 1)
+ *   qr_render_fetch(ctx, t, frame, stride)
+ *                              optional: start moving that frame to "frame" as
+ *                              soon as it is rendered and return at once -- by
+ *                              DMA straight into a page-locked frame (an
+ *                              application frame is page-locked on first sight
+ *                              unless QR_B200_PIN_FRAME=0), else into pinned
+ *                              staging; the caller overlaps its host work
  *   qr_render_end(ctx, t, frame, stride)
- *                              wait for that frame, copy it to "frame"
- *                              (geometry of the scene it was begun with;
- *                              frame == NULL: wait and drop)
+ *                              wait until "frame" holds that frame (fetching
+ *                              it now unless a fetch is under way; geometry of
+ *                              the scene it was begun with; frame == NULL:
+ *                              complete the fetch under way, or wait and drop)
  * At most two frames are in flight.  qr_pipeline(ctx, 0) drains and returns to
  * the synchronous protocol (upload, qr_render).
  */
 int qr_pipeline(qr_ctx *ctx, int on);
 int qr_render_begin(qr_ctx *ctx, int *ticket);
+int qr_render_fetch(qr_ctx *ctx, int ticket, uint32_t *frame, int stride);
 int qr_render_end(qr_ctx *ctx, int ticket, uint32_t *frame, int stride);
 
 /* Wait for all queued work of the context. */

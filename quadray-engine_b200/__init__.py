@@ -27,7 +27,7 @@ SYMBOLS = (
     "qr_render_device", "qr_render_rows", "qr_sync", "qr_frame_device",
     "qr_frame_ipc_export", "qr_frame_ipc_open", "qr_frame_ipc_close", "qr_dump_hits",
     "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
-    "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_end",
+    "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_fetch", "qr_render_end",
 )
 
 
@@ -82,6 +82,8 @@ def load_library():
     lib.qr_pipeline.restype = ci
     lib.qr_render_begin.argtypes = [vp, ctypes.POINTER(ci)]
     lib.qr_render_begin.restype = ci
+    lib.qr_render_fetch.argtypes = [vp, ci, vp, ci]
+    lib.qr_render_fetch.restype = ci
     lib.qr_render_end.argtypes = [vp, ci, vp, ci]
     lib.qr_render_end.restype = ci
     lib.qr_sync.restype = ci
@@ -183,8 +185,17 @@ class Context(object):
         self._check(self.lib.qr_render_begin(self.h, ctypes.byref(t)))
         return (t.value, dict(self.header))
 
-    def render_end(self, ticket, frame=None):
+    def render_fetch(self, ticket, frame):
+        """Start delivering the frame of "ticket" into "frame"; returns at once."""
+        t, _ = ticket
+        self._check(self.lib.qr_render_fetch(self.h, t, _ptr(frame), frame.strides[0] // 4))
+
+    def render_end(self, ticket, frame=None, fetched=False):
+        """Wait for the frame of "ticket"; fetched=True completes a render_fetch."""
         t, h = ticket
+        if fetched:
+            self._check(self.lib.qr_render_end(self.h, t, None, 0))
+            return frame
         if frame is None:
             frame = np.zeros((h["y_res"], h["x_res"]), dtype=np.uint32)
         self._check(self.lib.qr_render_end(self.h, t, _ptr(frame), frame.strides[0] // 4))

@@ -86,6 +86,7 @@ static qr_ctx      *g_ctx = RT_NULL;
 static qr_Flattener g_flat;
 static char         g_err[600];
 static bool         g_pipelined = false;
+static double       g_tb = 0.0;         /* QR_B200_TIMING: frame queued at */
 
 /* pipelined mode: the frame in flight and the buffer it belongs to */
 static struct
@@ -186,6 +187,16 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     static unsigned frame_no = 0;
     const double t0 = timing ? qr_now_ms() : 0.0;
 
+    /* pipelined mode: the previous frame starts its way into the caller's
+     * buffer now, so the transfer runs beside the flattening and packing */
+    const bool same = g_prev.frame == s_inf->frame && g_prev.row == s_inf->frm_row
+                   && g_prev.w == s_inf->frm_w && g_prev.h == s_inf->frm_h;
+    if (g_pipelined && g_prev.ticket >= 0 && same
+    &&  qr_render_fetch(g_ctx, g_prev.ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
+    {
+        qr_throw("B200 frame fetch failed", g_ctx);
+    }
+
     size_t bytes = 0;
     const uint8_t *blob = g_flat.build(s_inf, &bytes);
     const double t1 = timing ? qr_now_ms() : 0.0;
@@ -209,13 +220,13 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
         {
             qr_throw("B200 render failed", g_ctx);
         }
-        const bool same = g_prev.frame == s_inf->frame && g_prev.row == s_inf->frm_row
-                       && g_prev.w == s_inf->frm_w && g_prev.h == s_inf->frm_h;
+        g_tb = timing ? qr_now_ms() : 0.0;
         int rc = QR_OK;
         if (g_prev.ticket >= 0)
         {
-            rc = same ? qr_render_end(g_ctx, g_prev.ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row)
-                      : qr_render_end(g_ctx, g_prev.ticket, RT_NULL, 0);
+            /* completes the fetch started above, or drops a frame that belongs
+             * to another buffer / geometry */
+            rc = qr_render_end(g_ctx, g_prev.ticket, RT_NULL, 0);
             g_prev.ticket = -1;
         }
         if (rc == QR_OK && !same)
@@ -240,11 +251,22 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     {
         qr_throw("B200 render failed", g_ctx);
     }
+    static double t_last = 0.0;
     if (timing && (frame_no++ & 63) == 8)
     {
         const double t3 = qr_now_ms();
+        if (g_pipelined)
+        {
+            fprintf(stderr, "B200 render0 (pipelined): since last render0 %.3f ms (engine update + app), "
+                            "queue frame %.3f ms, collect previous frame %.3f ms\n",
+                            t0 - t_last, g_tb - t2, t3 - g_tb);
+        }
         fprintf(stderr, "B200 render0: flatten %.3f ms, upload %.3f ms, render + frame copy %.3f ms "
                         "(blob %u bytes)\n", t1 - t0, t2 - t1, t3 - t2, (unsigned)bytes);
+    }
+    if (timing)
+    {
+        t_last = qr_now_ms();
     }
 }
 

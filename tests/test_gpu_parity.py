@@ -253,6 +253,32 @@ def test_gpu_multi_device_context(entry, pkg):
             c.close()
 
 
+def test_gpu_multi_device_4k_and_pipelined(entry, pkg):
+    """BASELINE.json config 4: the 3840x2160 4xAA demo frame tile-row-sharded
+    over the GPUs of one context (NVLink framebuffer gather), synchronous and
+    pipelined; every row has the reference's CRC.  Needs >= 2 devices."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    blob, rowcrc, meta = entry.load_golden_hashed("demo03_4k_a4gh")
+    small, ref, _ = entry.load_golden("test17_full_a4")
+    c = pkg.Context(list(range(n)))
+    try:
+        c.upload(blob)
+        got = c.render_frame()
+        assert np.array_equal(entry.row_crcs(got), rowcrc), meta["args"]
+        c.pipeline(True)
+        c.upload(blob)
+        ta = c.render_begin()
+        c.upload(small)
+        tb = c.render_begin()
+        assert np.array_equal(entry.row_crcs(c.render_end(ta)), rowcrc)
+        assert np.array_equal(c.render_end(tb), ref)
+    finally:
+        c.close()
+
+
 def test_gpu_pipelined_frames(entry, pkg):
     """qr_pipeline / qr_render_begin / qr_render_end: two frames of different
     scenes and geometries in flight, each collected frame is the reference's;
@@ -285,6 +311,18 @@ def test_gpu_pipelined_frames(entry, pkg):
         with pytest.raises(pkg.QuadRayError):
             c.render_end(ta)
         assert np.array_equal(c.render_end(tb), ref)
+        # fetch: the transfer starts early and runs beside the caller's work;
+        # into a pageable frame (helper thread) and into a page-locked one (DMA)
+        import torch
+        c.upload(blob); tc = c.render_begin()
+        pageable = np.zeros_like(ref)
+        c.render_fetch(tc, pageable)
+        c.upload(blob); td = c.render_begin()
+        assert np.array_equal(c.render_end(tc, pageable, fetched=True), ref)
+        pinned = torch.zeros(ref.shape, dtype=torch.int32).pin_memory()
+        pv = pinned.numpy().view(np.uint32)
+        c.render_fetch(td, pv)
+        assert np.array_equal(c.render_end(td, pv, fetched=True), ref)
         # back to the synchronous protocol
         c.pipeline(False)
         c.upload(blob)
