@@ -27,6 +27,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <new>
+#include <sched.h>
 #include <thread>
 #include <mutex>
 #include <condition_variable>
@@ -1240,6 +1241,15 @@ static void qr_copy_rows(uint32_t *dst, int st, const uint32_t *src, const qr_bl
 
 static void qr_helper_main(qr_ctx *ctx)
 {
+    {
+        /* the thread that switches pipelining on is typically a worker pinned
+         * to one core (root/RooT_linux.cpp:681-699); the helper must not share
+         * that core with it */
+        cpu_set_t all;
+        CPU_ZERO(&all);
+        for (int i = 0; i < CPU_SETSIZE; i++) CPU_SET(i, &all);
+        sched_setaffinity(0, sizeof(all), &all);
+    }
     cudaSetDevice(ctx->dev[0].id);
     std::unique_lock<std::mutex> lk(ctx->hmtx);
     for (;;)
