@@ -64,6 +64,9 @@ int32_t qr_Flattener::surface(const rt_SIMD_SURFACE *s)
     if (idx == next)
     {
         surf_src.push_back(s);
+        /* what the element loop asks of a surface, kept beside the index so
+         * the loop does not touch the 4.7 KB record once per element */
+        surf_array.push_back(s->srf_t[3] < 0);
     }
     return idx;
 }
@@ -182,7 +185,7 @@ void qr_Flattener::drain()
                 r.data_i = (int32_t)(e->data & 3);
                 const rt_ELEM *last = (const rt_ELEM *)(e->data & ~(rt_cell)3);
                 if (last != RT_NULL && s != RT_NULL
-                &&  (r.data_i == 1 || s->srf_t[3] < 0))
+                &&  (r.data_i == 1 || surf_array[(size_t)r.simd]))
                 {
                     r.data_p = list_head(last, LIST_SURF);
                 }
@@ -197,7 +200,7 @@ void qr_Flattener::drain()
             {
                 const rt_SIMD_SURFACE *s = (const rt_SIMD_SURFACE *)e->simd;
                 r.simd = surface(s);
-                if (s != RT_NULL && s->srf_t[3] < 0)
+                if (s != RT_NULL && surf_array[(size_t)r.simd])
                 {
                     r.data_p = list_head((const rt_ELEM *)e->data, LIST_CLIP);
                 }
@@ -302,7 +305,7 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     {
         /* last frame's sizes are the best guess for this frame's */
         const size_t ne = elem_src.size() + 1024;
-        elem_src.clear(); elem_kind.clear(); surf_src.clear();
+        elem_src.clear(); elem_kind.clear(); surf_src.clear(); surf_array.clear();
         elem_src.reserve(ne); elem_kind.reserve(ne); elems.reserve(ne);
     }
     elems.clear(); surfs.clear(); mats.clear(); lgts.clear();

@@ -134,6 +134,7 @@ class qr_Flattener
     std::vector<const rt_ELEM *>            elem_src;
     std::vector<ListKind>                   elem_kind;
     std::vector<const rt_SIMD_SURFACE *>    surf_src;
+    std::vector<uint8_t>                    surf_array;     /* srf_t[3] < 0 per indexed surface */
     std::vector<PendingList>                pending;
 
     std::vector<qr_elem>        elems;
