@@ -353,6 +353,7 @@ struct qr_dev
     int             id;
     cudaStream_t    stream;
     cudaStream_t    copy;                           /* D2H of finished chunks (GPU 0) */
+    cudaStream_t    up;                             /* H2D of the next scene in pipelined mode */
     cudaEvent_t     ev0, ev1, done;
     cudaEvent_t     chunk_ev[QR_MAX_CHUNKS], copy_ev[QR_MAX_CHUNKS];
     /* scene image: two slots, so that in pipelined mode the scene of frame
@@ -482,6 +483,7 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         ||  (e = cudaGetDeviceProperties(&prop, d.id)) != cudaSuccess
         ||  (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess
         ||  (e = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking)) != cudaSuccess
+        ||  (e = cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking)) != cudaSuccess
         ||  (e = cudaEventCreate(&d.ev0)) != cudaSuccess
         ||  (e = cudaEventCreate(&d.ev1)) != cudaSuccess
         ||  (e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming)) != cudaSuccess
@@ -591,6 +593,7 @@ extern "C" void qr_shutdown(qr_ctx *ctx)
         cudaSetDevice(d.id);
         if (d.stream)  { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
         if (d.copy)    { cudaStreamSynchronize(d.copy); cudaStreamDestroy(d.copy); }
+        if (d.up)      { cudaStreamSynchronize(d.up); cudaStreamDestroy(d.up); }
         for (int k = 0; k < QR_MAX_CHUNKS; k++)
         {
             if (d.chunk_ev[k]) cudaEventDestroy(d.chunk_ev[k]);
@@ -739,7 +742,18 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         {
             return rc;
         }
-        QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d[sl], d0.blob_h[sl], n, cudaMemcpyHostToDevice, d.stream));
+        if (ctx->pipelined)
+        {
+            /* the slot is free (waited for above): copy on the copy stream, beside
+             * the kernels of the frame in flight; the next kernel waits for it */
+            QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d[sl], d0.blob_h[sl], n, cudaMemcpyHostToDevice, d.up));
+            QR_CUDA(ctx, cudaEventRecord(d.done, d.up));
+            QR_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.done, 0));
+        }
+        else
+        {
+            QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d[sl], d0.blob_h[sl], n, cudaMemcpyHostToDevice, d.stream));
+        }
     }
 
     ctx->hdr = *h;
