@@ -122,8 +122,6 @@ class qr_Flattener
 
     enum ListKind { LIST_SURF = 0, LIST_LIGHT = 1, LIST_CLIP = 2 };
 
-    struct PendingList { const rt_ELEM *head; ListKind kind; };
-
     int32_t     list_head(const rt_ELEM *head, ListKind kind);
     int32_t     surface(const rt_SIMD_SURFACE *s);
     int32_t     material(const rt_SIMD_MATERIAL *m);
@@ -135,7 +133,6 @@ class qr_Flattener
     std::vector<ListKind>                   elem_kind;
     std::vector<const rt_SIMD_SURFACE *>    surf_src;
     std::vector<uint8_t>                    surf_array;     /* srf_t[3] < 0 per indexed surface */
-    std::vector<PendingList>                pending;
 
     std::vector<qr_elem>        elems;
     std::vector<qr_surface>     surfs;
