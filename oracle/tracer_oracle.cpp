@@ -66,7 +66,22 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     }
 
     size_t bytes = 0;
+    static double flat_ms = 0.0;
+    static int flat_n = 0;
+    timeval fa, fb;
+    gettimeofday(&fa, NULL);
     const uint8_t *blob = g_flat.build(s_inf, &bytes);
+    gettimeofday(&fb, NULL);
+    /* QR_FLATTEN_TIME=1: running mean of the flattener's time per frame, as the
+     * product pays it (lists fresh from the update phases on other cores) */
+    if (getenv("QR_FLATTEN_TIME") != NULL)
+    {
+        flat_ms += (fb.tv_sec - fa.tv_sec) * 1e3 + (fb.tv_usec - fa.tv_usec) / 1e3;
+        if ((++flat_n % 50) == 0)
+        {
+            fprintf(stderr, "flatten: mean %.3f ms over %d frames\n", flat_ms / flat_n, flat_n);
+        }
+    }
 
     /* QR_FLATTEN_REPEAT=n: time n more flattener passes of this frame (the
      * product's host-side cost, measurable without a GPU) */

@@ -25,32 +25,48 @@
 
 #define QR_FIELD (RT_SIMD_QUADS * 16)   /* bytes of one SIMD field */
 
+/*
+ * The lists and SIMD structs were written a moment ago by the update phases on
+ * OTHER cores, so nearly every record this thread touches is a cache-to-cache
+ * miss; what can be named ahead of time is prefetched.
+ */
+#if defined(__GNUC__)
+#define QR_PREFETCH(p) __builtin_prefetch((p), 0, 1)
+#else
+#define QR_PREFETCH(p) ((void)0)
+#endif
+
+static inline void qr_prefetch_range(const void *p, size_t bytes)
+{
+    const char *c = (const char *)p;
+    for (size_t o = 0; o < bytes; o += 64)
+    {
+        QR_PREFETCH(c + o);
+    }
+}
+
+/*
+ * Index of a list element, assigned on first sight.  Elements are only NAMED
+ * here and read later, in index order, by drain(): every record is then
+ * known a few iterations before it is read and can be prefetched, and no
+ * chain is chased through cold memory.  (The blob's element order is
+ * breadth-first as a result; the kernel image re-sequences the lists anyway,
+ * qr_kscene.h.)
+ */
 int32_t qr_Flattener::list_head(const rt_ELEM *head, ListKind kind)
 {
     if (head == RT_NULL)
     {
         return QR_NIL;
     }
-
-    int32_t first = elem_idx.find(head);
-    if (first >= 0)
+    const int32_t next = (int32_t)elem_src.size();
+    const int32_t idx = elem_idx.insert(head, next);
+    if (idx == next)
     {
-        return first;
-    }
-
-    /* index the whole chain consecutively, stop at a shared tail */
-    first = (int32_t)elem_src.size();
-    for (const rt_ELEM *e = head; e != RT_NULL; e = e->next)
-    {
-        const int32_t next = (int32_t)elem_src.size();
-        if (elem_idx.insert(e, next) != next)
-        {
-            break;
-        }
-        elem_src.push_back(e);
+        elem_src.push_back(head);
         elem_kind.push_back(kind);
     }
-    return first;
+    return idx;
 }
 
 int32_t qr_Flattener::surface(const rt_SIMD_SURFACE *s)
@@ -170,13 +186,17 @@ void qr_Flattener::drain()
     {
         for (; elem_done < elem_src.size(); elem_done++)
         {
+            if (elem_done + 8 < elem_src.size())
+            {
+                QR_PREFETCH(elem_src[elem_done + 8]);
+            }
             const rt_ELEM *e = elem_src[elem_done];
             ListKind kind = elem_kind[elem_done];
             qr_elem r;
             r.data_i = 0;
             r.data_p = QR_NIL;
             r.simd   = QR_NIL;
-            r.next   = QR_NIL;
+            r.next   = list_head(e->next, kind);
 
             if (kind == LIST_SURF)
             {
@@ -215,6 +235,18 @@ void qr_Flattener::drain()
 
         for (; surf_done < surf_src.size(); surf_done++)
         {
+            /* two records ahead: the surface; one ahead (its pointers are in
+             * cache by now): its two materials */
+            if (surf_done + 2 < surf_src.size())
+            {
+                qr_prefetch_range(surf_src[surf_done + 2], sizeof(rt_SIMD_SURFACE));
+            }
+            if (surf_done + 1 < surf_src.size())
+            {
+                const rt_SIMD_SURFACE *n = surf_src[surf_done + 1];
+                if (n->mat_p[0] != RT_NULL) qr_prefetch_range(n->mat_p[0], sizeof(rt_SIMD_MATERIAL));
+                if (n->mat_p[2] != RT_NULL) qr_prefetch_range(n->mat_p[2], sizeof(rt_SIMD_MATERIAL));
+            }
             const rt_SIMD_SURFACE *s = surf_src[surf_done];
             qr_surface r;
             memset(&r, 0, sizeof(r));
@@ -270,15 +302,6 @@ void qr_Flattener::drain()
         }
     }
 
-    /* "next" links once every element has its index */
-    for (size_t i = 0; i < elems.size(); i++)
-    {
-        const rt_ELEM *n = elem_src[i]->next;
-        /* chains are indexed consecutively: the successor is nearly always i + 1 */
-        elems[i].next = n == RT_NULL ? QR_NIL
-                      : (i + 1 < elems.size() && elem_src[i + 1] == n) ? (int32_t)(i + 1)
-                      : elem_idx.find(n);
-    }
 }
 
 static uint32_t align16(uint32_t v)
@@ -372,6 +395,10 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     tiles.resize(n_tiles);
     for (int32_t t = 0; t < n_tiles; t++)
     {
+        if (t + 8 < n_tiles && tl[t + 8] != RT_NULL)
+        {
+            QR_PREFETCH(tl[t + 8]);
+        }
         tiles[t] = list_head(tl[t], LIST_SURF);
     }
     drain();

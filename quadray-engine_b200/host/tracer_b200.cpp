@@ -251,18 +251,30 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     {
         qr_throw("B200 render failed", g_ctx);
     }
-    static double t_last = 0.0;
-    if (timing && (frame_no++ & 63) == 8)
+    static double t_last = 0.0, sum[6] = { 0, 0, 0, 0, 0, 0 };
+    if (timing)
     {
+        /* running means over all frames but the first few (warm-up), printed
+         * every 64th frame */
         const double t3 = qr_now_ms();
-        if (g_pipelined)
+        if (frame_no >= 8)
         {
-            fprintf(stderr, "B200 render0 (pipelined): since last render0 %.3f ms (engine update + app), "
-                            "queue frame %.3f ms, collect previous frame %.3f ms\n",
-                            t0 - t_last, g_tb - t2, t3 - g_tb);
+            sum[0] += t1 - t0; sum[1] += t2 - t1; sum[2] += t3 - t2;
+            sum[3] += t0 - t_last; sum[4] += g_tb - t2; sum[5] += t3 - g_tb;
         }
-        fprintf(stderr, "B200 render0: flatten %.3f ms, upload %.3f ms, render + frame copy %.3f ms "
-                        "(blob %u bytes)\n", t1 - t0, t2 - t1, t3 - t2, (unsigned)bytes);
+        if (frame_no >= 8 && ((frame_no - 7) & 63) == 0)
+        {
+            const double n = (double)(frame_no - 7);
+            if (g_pipelined)
+            {
+                fprintf(stderr, "B200 render0 (pipelined, mean of %d): since last render0 %.3f ms (engine update + app), "
+                                "queue frame %.3f ms, collect previous frame %.3f ms\n",
+                                (int)n, sum[3] / n, sum[4] / n, sum[5] / n);
+            }
+            fprintf(stderr, "B200 render0 (mean of %d): flatten %.3f ms, upload %.3f ms, render + frame copy %.3f ms "
+                            "(blob %u bytes)\n", (int)n, sum[0] / n, sum[1] / n, sum[2] / n, (unsigned)bytes);
+        }
+        frame_no++;
     }
     if (timing)
     {
