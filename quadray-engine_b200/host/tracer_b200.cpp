@@ -92,10 +92,11 @@ static double       g_tb = 0.0;         /* QR_B200_TIMING: frame queued at */
 static struct
 {
     int      ticket;
+    bool     fetching;
     rt_pntr  frame;
     rt_si32  row, w, h;
 }
-g_prev = { -1, RT_NULL, 0, 0, 0 };
+g_prev = { -1, false, RT_NULL, 0, 0, 0 };
 
 static double qr_now_ms()
 {
@@ -191,10 +192,15 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
      * buffer now, so the transfer runs beside the flattening and packing */
     const bool same = g_prev.frame == s_inf->frame && g_prev.row == s_inf->frm_row
                    && g_prev.w == s_inf->frm_w && g_prev.h == s_inf->frm_h;
-    if (g_pipelined && g_prev.ticket >= 0 && same
-    &&  qr_render_fetch(g_ctx, g_prev.ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
+    if (g_pipelined && g_prev.ticket >= 0 && same && !g_prev.fetching)
     {
-        qr_throw("B200 frame fetch failed", g_ctx);
+        /* (a frame stays "fetching" if a later step of that call threw: the
+         * next call completes it instead of starting it again) */
+        if (qr_render_fetch(g_ctx, g_prev.ticket, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
+        {
+            qr_throw("B200 frame fetch failed", g_ctx);
+        }
+        g_prev.fetching = true;
     }
 
     size_t bytes = 0;
@@ -228,6 +234,7 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
              * to another buffer / geometry */
             rc = qr_render_end(g_ctx, g_prev.ticket, RT_NULL, 0);
             g_prev.ticket = -1;
+            g_prev.fetching = false;
         }
         if (rc == QR_OK && !same)
         {
