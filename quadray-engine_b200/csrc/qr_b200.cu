@@ -204,8 +204,6 @@ qr_render_kernel(const qr_launch p)
 
     while (item < n_items)
     {
-        unsigned int next = 0;
-        if (lane == 0) next = atomicAdd(p.queue, 1u);
 
         const unsigned int tile = item / per_tile;
         const unsigned int sub  = item % per_tile;
@@ -285,7 +283,12 @@ qr_render_kernel(const qr_launch p)
                 }
             }
         }
-        item = __shfl_sync(0xFFFFFFFFu, next, 0);
+        /* drawn when it is needed, not one item ahead: an item reserved early
+         * waits behind the one in progress while other warps run dry, which
+         * doubles the tail of a launch; the atomic's latency is hidden by the
+         * other warps of the SM */
+        if (lane == 0) item = atomicAdd(p.queue, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
     }
 
     /* ray counters: warp-reduce, one atomic per warp and kind */
