@@ -181,6 +181,37 @@ def test_gpu_unstaged_scene_variant(entry, pkg):
     assert p.returncode == 0 and b"ok" in p.stdout, p.stdout.decode(errors="replace")[-2000:]
 
 
+@pytest.mark.parametrize("shape", ["7", "3", "6"])
+def test_gpu_every_fixture_at_the_big_frame_launch_shapes(entry, pkg, shape):
+    """Big frames run 1024-thread CTAs at 64 registers (chosen by frame size);
+    forced here (and the 768 / 896-thread shapes) on EVERY small fixture, so
+    each feature of the path -- custom clippers, conic fix-up, transform nodes,
+    refraction -- is also checked in that build of the kernel, staged and
+    unstaged: the frames are the reference's."""
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN_SMALL
+    code = (
+        "import sys, os; sys.path.insert(0, %r)\n"
+        "import numpy as np, __graft_entry__ as ge\n"
+        "pkg = ge.load_package(); c = pkg.Context([0])\n"
+        "for name in %r:\n"
+        "    blob, ref, meta = ge.load_golden(name)\n"
+        "    c.upload(blob); got = c.render_frame()\n"
+        "    assert c.kernel_info()['threads_per_cta'] == %d\n"
+        "    assert int((got != ref).sum()) == 0, name\n"
+        "c.close(); print('ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                        list(GOLDEN_SMALL), {"7": 1024, "3": 768, "6": 896}[shape])
+    for nostage in ("0", "1") if shape == "7" else ("0",):
+        env = dict(os.environ)
+        env["QR_B200_SHAPE"] = shape
+        env["QR_B200_NOSTAGE"] = nostage
+        p = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           timeout=900)
+        assert p.returncode == 0 and b"ok" in p.stdout, p.stdout.decode(errors="replace")[-2000:]
+
+
 def test_gpu_render_is_deterministic(entry, ctx):
     blob, _, _ = entry.load_golden("demo02_a4g")
     ctx.upload(blob)
