@@ -380,6 +380,15 @@ struct qr_dev
     bool            timed;
 };
 
+/* rows [ya, yb) of a frame in pinned staging, to be copied to the caller once "ev" has passed */
+struct qr_copy_job
+{
+    uint32_t       *dst;
+    const uint32_t *src;
+    int             st, dstride, x_res, ya, yb;
+    cudaEvent_t     ev;
+};
+
 struct qr_ctx
 {
     int             ndev;
@@ -401,7 +410,9 @@ struct qr_ctx
     int             fetching[2];    /* 0 not yet, 1 DMA into the caller's frame, 2 DMA into pinned staging */
     uint32_t       *fetch_dst[2];   /* where qr_render_fetch was told to put it */
     int             fetch_stride[2];
-    std::thread     helper[QR_COPY_THREADS];    /* pipelined mode: staging -> caller's frame copies */
+    bool            fetch_posted[2];
+    std::thread     helper[QR_COPY_THREADS];    /* staging -> caller's pageable frame copies */
+    qr_copy_job     job[2];
     int             nhelper;
     std::mutex      hmtx;
     std::condition_variable hcv;
@@ -901,6 +912,137 @@ static int qr_collect_rays(qr_ctx *ctx)
     return QR_OK;
 }
 
+/* is "frame" page-locked by its owner (so the copy engine can write it)? */
+static bool qr_frame_pinned(uint32_t *frame)
+{
+    cudaPointerAttributes at;
+    const bool yes = cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+}
+
+/*
+ * Helper threads: copy a frame (or a chunk of rows) that arrived in pinned
+ * staging into the caller's pageable frame -- the engine's own frame, RooT's
+ * XShm image.  One thread moves ~11 GB/s, i.e. a 1080p frame in 0.75 ms; four
+ * of them 0.25 ms, and in pipelined mode they do it while the caller flattens
+ * and uploads the next scene.  Two job slots.
+ */
+static void qr_copy_rows(const qr_copy_job &j, int part = 0, int parts = 1)
+{
+    const size_t wbytes = (size_t)j.x_res * sizeof(uint32_t);
+    const int n = j.yb - j.ya;
+    const int ya = j.ya + (int)((long long)n * part / parts), yb = j.ya + (int)((long long)n * (part + 1) / parts);
+    if (j.st == j.dstride && j.st == j.x_res)
+    {
+        memcpy(j.dst + (size_t)ya * j.st, j.src + (size_t)ya * j.dstride, wbytes * (size_t)(yb - ya));
+        return;
+    }
+    for (int y = ya; y < yb; y++)
+    {
+        memcpy(j.dst + (ptrdiff_t)y * j.st, j.src + (size_t)y * j.dstride, wbytes);
+    }
+}
+
+static void qr_helper_main(qr_ctx *ctx, int k)
+{
+    {
+        /* the thread that starts the helpers is typically a worker pinned to
+         * one core (root/RooT_linux.cpp:681-699); they must not share that
+         * core with it */
+        cpu_set_t all;
+        CPU_ZERO(&all);
+        for (int i = 0; i < CPU_SETSIZE; i++) CPU_SET(i, &all);
+        sched_setaffinity(0, sizeof(all), &all);
+    }
+    cudaSetDevice(ctx->dev[0].id);
+    std::unique_lock<std::mutex> lk(ctx->hmtx);
+    for (;;)
+    {
+        int t = -1;
+        ctx->hcv.wait(lk, [ctx, k, &t]
+        {
+            if (ctx->hquit) return true;
+            for (int s = 0; s < 2; s++)
+            {
+                if (ctx->hjob[s] == 1 && !ctx->htaken[s][k]) { t = s; return true; }
+            }
+            return false;
+        });
+        if (ctx->hquit)
+        {
+            return;
+        }
+        ctx->htaken[t][k] = true;
+        const qr_copy_job j = ctx->job[t];
+        lk.unlock();
+        /* every helper copies its band of the rows once they are in staging */
+        const cudaError_t e = cudaEventSynchronize(j.ev);
+        if (e == cudaSuccess)
+        {
+            qr_copy_rows(j, k, QR_COPY_THREADS);
+        }
+        lk.lock();
+        if (e != cudaSuccess) ctx->hfail[t] = true;
+        if (--ctx->hleft[t] == 0)
+        {
+            ctx->hjob[t] = ctx->hfail[t] ? 3 : 2;
+            ctx->hfail[t] = false;
+            memset(ctx->htaken[t], 0, sizeof(ctx->htaken[t]));
+            ctx->hcv.notify_all();
+        }
+    }
+}
+
+static void qr_helpers_start(qr_ctx *ctx)
+{
+    if (ctx->nhelper > 0)
+    {
+        return;
+    }
+    ctx->hquit = false;
+    ctx->hjob[0] = ctx->hjob[1] = 0;
+    memset(ctx->htaken, 0, sizeof(ctx->htaken));
+    for (int k = 0; k < QR_COPY_THREADS; k++)
+    {
+        ctx->helper[k] = std::thread(qr_helper_main, ctx, k);
+    }
+    ctx->nhelper = QR_COPY_THREADS;
+}
+
+/* hand job "j" to the helpers in slot t; false when the slot is busy */
+static bool qr_helpers_post(qr_ctx *ctx, int t, const qr_copy_job &j)
+{
+    if (ctx->nhelper == 0)
+    {
+        return false;
+    }
+    std::lock_guard<std::mutex> lk(ctx->hmtx);
+    if (ctx->hjob[t] != 0)
+    {
+        return false;
+    }
+    ctx->job[t] = j;
+    ctx->hjob[t] = 1;
+    ctx->hleft[t] = ctx->nhelper;
+    ctx->hcv.notify_all();
+    return true;
+}
+
+/* wait for slot t: 1 copied, 0 nothing was posted, -1 failed */
+static int qr_helpers_wait(qr_ctx *ctx, int t)
+{
+    std::unique_lock<std::mutex> lk(ctx->hmtx);
+    if (ctx->hjob[t] == 0)
+    {
+        return 0;
+    }
+    ctx->hcv.wait(lk, [ctx, t] { return ctx->hjob[t] >= 2; });
+    const int r = ctx->hjob[t] == 2 ? 1 : -1;
+    ctx->hjob[t] = 0;
+    return r;
+}
+
 static int qr_frame_ensure(qr_ctx *ctx)
 {
     const qr_blob_header &h = ctx->hdr;
@@ -1158,8 +1300,35 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
                                        wbytes, (size_t)(yb - ya), cudaMemcpyDeviceToHost, d0.copy));
         QR_CUDA(ctx, cudaEventRecord(d0.copy_ev[k], d0.copy));
     }
+    /* out of staging into the caller's pageable frame: by the helper threads,
+     * chunk by chunk as the copies land (two job slots), else on this thread */
+    bool posted[QR_MAX_CHUNKS];
+    for (int k = 0; k < nch; k++) posted[k] = false;
+    if (!direct && nch <= 2)
+    {
+        qr_helpers_start(ctx);
+        for (int k = 0; k < nch; k++)
+        {
+            const int ta = (int)((long long)h.tls_col * k / nch);
+            const int tb = (int)((long long)h.tls_col * (k + 1) / nch);
+            qr_copy_job j;
+            j.dst = frame; j.src = d0.frame_h; j.st = stride; j.dstride = dstride; j.x_res = h.x_res;
+            j.ya = ta * h.tile_h; j.yb = tb * h.tile_h;
+            if (j.yb > h.y_res) j.yb = h.y_res;
+            j.ev = d0.copy_ev[k];
+            posted[k] = qr_helpers_post(ctx, k, j);
+        }
+    }
     for (int k = 0; k < nch; k++)
     {
+        if (posted[k])
+        {
+            if (qr_helpers_wait(ctx, k) < 0)
+            {
+                return qr_fail(ctx, QR_E_CUDA, "qr_render: frame transfer failed");
+            }
+            continue;
+        }
         QR_CUDA(ctx, cudaEventSynchronize(d0.copy_ev[k]));
         if (!direct)
         {
@@ -1175,15 +1344,6 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     }
     return QR_OK;
 }
-
-/*
- * Pipelined frames (the host's update phases of frame
- * N + 1 run while the GPUs render frame N).  qr_render_begin queues the frame
- * of the scene uploaded last into an internal page-locked frame of its slot
- * and returns at once; qr_render_end waits for that frame and copies it out.
- * Two frames can be in flight; qr_scene_upload alternates the scene slot.
- */
-static void qr_helper_main(qr_ctx *ctx, int k);
 
 extern "C" int qr_pipeline(qr_ctx *ctx, int on)
 {
@@ -1223,100 +1383,11 @@ extern "C" int qr_pipeline(qr_ctx *ctx, int on)
         ctx->slot = 0;
     }
     ctx->pipelined = on != 0;
-    if (on && ctx->nhelper == 0)
+    if (on)
     {
-        ctx->hquit = false;
-        ctx->hjob[0] = ctx->hjob[1] = 0;
-        memset(ctx->htaken, 0, sizeof(ctx->htaken));
-        for (int k = 0; k < QR_COPY_THREADS; k++)
-        {
-            ctx->helper[k] = std::thread(qr_helper_main, ctx, k);
-        }
-        ctx->nhelper = QR_COPY_THREADS;
+        qr_helpers_start(ctx);
     }
     return QR_OK;
-}
-
-/* is "frame" page-locked by its owner (so the copy engine can write it)? */
-static bool qr_frame_pinned(uint32_t *frame)
-{
-    cudaPointerAttributes at;
-    const bool yes = cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    return yes;
-}
-
-/*
- * Pipelined mode's helper thread: copies a frame that arrived in pinned
- * staging into the caller's pageable frame while the caller flattens and
- * uploads the next scene (8.3 MB at 1080p: 0.75 ms on the caller's thread
- * otherwise).  One job at a time per slot.
- */
-static void qr_copy_rows(uint32_t *dst, int st, const uint32_t *src, const qr_blob_header &h,
-                         int part = 0, int parts = 1)
-{
-    const int dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
-    const size_t wbytes = (size_t)h.x_res * sizeof(uint32_t);
-    const int ya = (int)((long long)h.y_res * part / parts), yb = (int)((long long)h.y_res * (part + 1) / parts);
-    if (st == dstride && st == h.x_res)
-    {
-        memcpy(dst + (size_t)ya * st, src + (size_t)ya * dstride, wbytes * (size_t)(yb - ya));
-        return;
-    }
-    for (int y = ya; y < yb; y++)
-    {
-        memcpy(dst + (ptrdiff_t)y * st, src + (size_t)y * dstride, wbytes);
-    }
-}
-
-static void qr_helper_main(qr_ctx *ctx, int k)
-{
-    {
-        /* the thread that switches pipelining on is typically a worker pinned
-         * to one core (root/RooT_linux.cpp:681-699); the helpers must not share
-         * that core with it */
-        cpu_set_t all;
-        CPU_ZERO(&all);
-        for (int i = 0; i < CPU_SETSIZE; i++) CPU_SET(i, &all);
-        sched_setaffinity(0, sizeof(all), &all);
-    }
-    cudaSetDevice(ctx->dev[0].id);
-    std::unique_lock<std::mutex> lk(ctx->hmtx);
-    for (;;)
-    {
-        int t = -1;
-        ctx->hcv.wait(lk, [ctx, k, &t]
-        {
-            if (ctx->hquit) return true;
-            for (int s = 0; s < 2; s++)
-            {
-                if (ctx->hjob[s] == 1 && !ctx->htaken[s][k]) { t = s; return true; }
-            }
-            return false;
-        });
-        if (ctx->hquit)
-        {
-            return;
-        }
-        ctx->htaken[t][k] = true;
-        lk.unlock();
-        /* every helper copies its band of rows once the frame is in staging */
-        const cudaError_t e = cudaEventSynchronize(ctx->dev[0].fetch_ev[t]);
-        if (e == cudaSuccess)
-        {
-            qr_copy_rows(ctx->fetch_dst[t], ctx->fetch_stride[t], ctx->dev[0].frame_p[t], ctx->pend_hdr[t],
-                         k, QR_COPY_THREADS);
-        }
-        lk.lock();
-        if (e != cudaSuccess) ctx->hfail[t] = true;
-        if (--ctx->hleft[t] == 0)
-        {
-            ctx->hjob[t] = ctx->hfail[t] ? 3 : 2;
-            ctx->hfail[t] = false;
-            memset(ctx->htaken[t], 0, sizeof(ctx->htaken[t]));
-            ctx->hcv.notify_all();
-        }
-    }
 }
 
 extern "C" int qr_render_begin(qr_ctx *ctx, int *ticket)
@@ -1445,13 +1516,13 @@ extern "C" int qr_render_fetch(qr_ctx *ctx, int ticket, uint32_t *frame, int str
     QR_CUDA(ctx, cudaEventRecord(d0.fetch_ev[ticket], d0.copy));
     ctx->fetch_dst[ticket] = frame;
     ctx->fetch_stride[ticket] = stride;
-    if (ctx->fetching[ticket] == 2 && ctx->nhelper > 0)
+    if (ctx->fetching[ticket] == 2)
     {
         /* the helper threads take the frame from staging to the caller */
-        std::lock_guard<std::mutex> lk(ctx->hmtx);
-        ctx->hjob[ticket] = 1;
-        ctx->hleft[ticket] = ctx->nhelper;
-        ctx->hcv.notify_all();
+        qr_copy_job j;
+        j.dst = frame; j.src = d0.frame_p[ticket]; j.st = stride; j.dstride = dstride;
+        j.x_res = h.x_res; j.ya = 0; j.yb = h.y_res; j.ev = d0.fetch_ev[ticket];
+        ctx->fetch_posted[ticket] = qr_helpers_post(ctx, ticket, j);
     }
     return QR_OK;
 }
@@ -1489,25 +1560,26 @@ extern "C" int qr_render_end(qr_ctx *ctx, int ticket, uint32_t *frame, int strid
         return qr_fail(ctx, QR_E_ARG, "qr_render_end: the frame is being fetched into another buffer");
     }
     bool copied = false;
+    if (ctx->fetching[ticket] == 2 && ctx->fetch_posted[ticket])
     {
-        std::unique_lock<std::mutex> lk(ctx->hmtx);
-        if (ctx->hjob[ticket] != 0)
+        ctx->fetch_posted[ticket] = false;
+        if (qr_helpers_wait(ctx, ticket) < 0)
         {
-            ctx->hcv.wait(lk, [ctx, ticket] { return ctx->hjob[ticket] >= 2; });
-            copied = ctx->hjob[ticket] == 2;
-            ctx->hjob[ticket] = 0;
-            if (!copied)
-            {
-                return qr_fail(ctx, QR_E_CUDA, "qr_render_end: frame transfer failed");
-            }
+            return qr_fail(ctx, QR_E_CUDA, "qr_render_end: frame transfer failed");
         }
+        copied = true;
     }
     if (!copied)
     {
         QR_CUDA(ctx, cudaEventSynchronize(d0.fetch_ev[ticket]));
         if (ctx->fetching[ticket] == 2)
         {
-            qr_copy_rows(ctx->fetch_dst[ticket], ctx->fetch_stride[ticket], d0.frame_p[ticket], ctx->pend_hdr[ticket]);
+            const qr_blob_header &h = ctx->pend_hdr[ticket];
+            qr_copy_job j;
+            j.dst = ctx->fetch_dst[ticket]; j.src = d0.frame_p[ticket]; j.st = ctx->fetch_stride[ticket];
+            j.dstride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+            j.x_res = h.x_res; j.ya = 0; j.yb = h.y_res; j.ev = NULL;
+            qr_copy_rows(j);
         }
     }
     ctx->pending[ticket] = false;
