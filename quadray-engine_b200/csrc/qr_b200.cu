@@ -47,7 +47,7 @@ static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {38
 #define QR_N_SHAPES     8
 #define QR_DEFAULT_SHAPE 2
 #define QR_BIG_SHAPE     7          /* 1024 threads at 64 registers */
-#define QR_BIG_FRAME_ITEMS 150000   /* work items (32 samples each) per GPU from which QR_BIG_SHAPE pays */
+#define QR_BIG_FRAME_ITEMS 60000    /* work items (32 samples each) per GPU from which QR_BIG_SHAPE pays */
 
 /* ------------------------------------------------------------------ PTX --- */
 
@@ -783,9 +783,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
      * Launch shape by the amount of work of a full-frame launch.  The walk is
      * latency-bound (dependent FP chains, list elements through L1/L2), so the
      * big frames want every warp slot of the SM even at 64 registers with a
-     * few spills (1080p 4xAA, RooT default scene: 1.90 ms at 1024 threads,
-     * 2.07 ms at 640); with few work items per warp the smaller CTA's cleaner
-     * code and finer tail win (800 x 480: 0.18 vs 0.22 ms on demo01).
+     * few spills (1080p 4xAA, RooT default scene: 1.87 ms at 1024 threads,
+     * 2.06 ms at 640; 1080p without AA, 65 k items: 0.53 vs 0.57 ms); with few
+     * work items per warp the smaller CTA's cleaner code and finer tail win
+     * (800 x 480 4xAA, 48 k items: 0.18 vs 0.22 ms on demo01).
      */
     if (!ctx->shape_fixed)
     {
