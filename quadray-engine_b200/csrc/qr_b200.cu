@@ -349,7 +349,8 @@ static qr_kernel_fn qr_kernel_of(bool staged, int shape)
 }
 
 #define QR_MAX_DEV 16
-#define QR_COPY_THREADS 4   /* one thread moves ~11 GB/s: a 1080p frame in 0.75 ms, four in 0.25 */
+#define QR_COPY_THREADS 16  /* upper bound; QR_B200_COPY_THREADS (default 4): one thread moves ~11 GB/s,
+                               a 1080p frame in 0.75 ms, four in 0.25 */
 #define QR_MAX_CHUNKS 8     /* qr_render to a host frame: render / D2H pipeline depth */
 
 struct qr_dev
@@ -981,7 +982,7 @@ static void qr_helper_main(qr_ctx *ctx, int k)
         const cudaError_t e = cudaEventSynchronize(j.ev);
         if (e == cudaSuccess)
         {
-            qr_copy_rows(j, k, QR_COPY_THREADS);
+            qr_copy_rows(j, k, ctx->nhelper);
         }
         lk.lock();
         if (e != cudaSuccess) ctx->hfail[t] = true;
@@ -1004,11 +1005,19 @@ static void qr_helpers_start(qr_ctx *ctx)
     ctx->hquit = false;
     ctx->hjob[0] = ctx->hjob[1] = 0;
     memset(ctx->htaken, 0, sizeof(ctx->htaken));
-    for (int k = 0; k < QR_COPY_THREADS; k++)
+    int n = 4;
+    {
+        const char *env = getenv("QR_B200_COPY_THREADS");
+        if (env != NULL && atoi(env) >= 1 && atoi(env) <= QR_COPY_THREADS)
+        {
+            n = atoi(env);
+        }
+    }
+    ctx->nhelper = n;           /* before the threads start: they divide the rows by it */
+    for (int k = 0; k < n; k++)
     {
         ctx->helper[k] = std::thread(qr_helper_main, ctx, k);
     }
-    ctx->nhelper = QR_COPY_THREADS;
 }
 
 /* hand job "j" to the helpers in slot t; false when the slot is busy */
