@@ -75,3 +75,34 @@ def test_oracle_rows_of_full_size_fixtures(entry, name):
     y0 = (meta["y_res"] // 2) & ~7
     got, _, _ = entry.oracle_render(blob, packet=32, y0=y0, y1=y0 + 4)
     assert np.array_equal(entry.row_crcs(got[y0:y0 + 4]), rowcrc[y0:y0 + 4]), meta["args"]
+
+
+
+
+@pytest.mark.parametrize("name", ["test12_full", "test03_full", "test16_none_a4", "demo02_a4g", "synth1k_a4",
+                                  "synth400_metal"])
+def test_flattener_of_this_tree_feeds_the_reference_frame(entry, tmp_path, name):
+    """Host logic without a GPU: the reference ENGINE + this tree's flattener
+    (quadray-engine_b200/host/qr_flatten.cpp) + the oracle, linked as
+    oracle/_ref/qr_oracle_harness, renders the reference's frame -- so a change
+    of the flattener (element order, prefetching, pointer map) is checked on
+    CPU before it meets a GPU.  The binary needs the reference's sources to be
+    built (build container); it is skipped where it does not exist."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "qr_oracle_harness")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/qr_oracle_harness was not built")
+    _, ref, meta = entry.load_golden(name)
+    out = str(tmp_path / "frame.raw")
+    env = dict(os.environ)
+    env["QR_ORACLE_PACKET"] = "32"
+    p = subprocess.run([exe] + meta["args"].split() + ["-o", out], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=600)
+    assert p.returncode == 0, p.stderr.decode()[-1000:]
+    info = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    got = np.fromfile(out, dtype=np.uint32).reshape(info["y_res"], info["x_res"])
+    assert got.shape == ref.shape
+    assert int((got != ref).sum()) == 0, meta["args"]
