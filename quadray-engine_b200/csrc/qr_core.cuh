@@ -637,7 +637,6 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
     const bool no_neg = !(t_min < 0.0f);
 
     t_buf = t_max;
-    bool found = false;
 
     uint32_t ei = head;
     qr_kelem e = v.elems[ei];
@@ -917,7 +916,6 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                     break;
                 }
                 t_buf = t;
-                found = true;
                 qr_sc_st(sc, QR_SC_BEST, qr_u2f(so | (uint32_t)side), lx, ly, lz);
                 break;
             }
@@ -937,7 +935,10 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
         e = en;
     }
 
-    return mode == QR_MODE_SHADOW ? false : found;
+    /* a hit lowered t_buf below the t_max the walk started from (the depth
+     * test is strict, 1602-1605), and a closest-hit walk always starts from
+     * the camera's: no flag to carry through the loop */
+    return mode == QR_MODE_SHADOW ? false : t_buf < v.h->cam_t_max;
 }
 
 /* texel -> linear colour, PAINT_COLX 664-673 */
