@@ -264,12 +264,13 @@ static void usage()
            "  [-t threads (0 = stub, sequential)] [-f frames] [-w warmup]\n"
            "  [-b time_begin_ms] [-d time_delta_ms] [-n simd -k size -v type]\n"
            "  [-u (freeze update after 1st frame: RT_OPTS_UPDATE_EXT0)]\n"
-           "  [-o out.raw (last frame, x_res*y_res u32)] [-q (quiet)]\n");
+           "  [-o out.raw (last frame, x_res*y_res u32)] [-q (quiet)]\n"
+           "  [-T t.raw (oracle/_ref/qr_ref_tdump only: primary hit distance per sample)]\n");
 }
 
 int main(int argc, char **argv)
 {
-    const char *scene_name = "test01", *out = NULL, *opts_s = "default";
+    const char *scene_name = "test01", *out = NULL, *opts_s = "default", *t_out = NULL;
     int x_res = 800, y_res = 480, fsaa = 0, threads = 0, frames = 1, warm = 0;
     int cam_idx = 0, n_simd = 0, k_size = 0, s_type = 0, quiet = 0;
     int gamma_on = 0, fresnel_on = 0, freeze = 0;
@@ -299,6 +300,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-v")) { s_type = atoi(v); i++; }
         else if (!strcmp(a, "-o")) { out = v; i++; }
         else if (!strcmp(a, "-q")) { quiet = 1; }
+        else if (!strcmp(a, "-T")) { t_out = v; i++; }
         else if (!strcmp(a, "-N")) { synth.n = atoi(v); i++; }
         else if (!strcmp(a, "-S")) { synth.seed = (unsigned)atol(v); i++; }
         else if (!strcmp(a, "-E")) { synth.extent = (float)atof(v); i++; }
@@ -402,6 +404,34 @@ int main(int argc, char **argv)
                 }
                 fclose(f);
             }
+        }
+
+        if (t_out != NULL)
+        {
+#ifdef QR_TDUMP
+            /* the patched reference of oracle/Makefile's tdump target left
+             * ctx_T_BUF(0) of every packet in the red plane:
+             * (y * x_row + x) << fsaa floats in, lanes in packet order */
+            FILE *f = fopen(t_out, "wb");
+            rt_real *tb = scene->qr_tbuf();
+            if (f == NULL || tb == NULL)
+            {
+                fprintf(stderr, "cannot dump T to %s\n", t_out);
+                rc = 1;
+            }
+            else
+            {
+                int row = scene->get_x_row();
+                for (int y = 0; y < y_res; y++)
+                {
+                    fwrite(tb + (((size_t)y * row) << fsaa), sizeof(rt_real), (size_t)x_res << fsaa, f);
+                }
+            }
+            if (f != NULL) fclose(f);
+#else
+            fprintf(stderr, "-T needs the tdump build (oracle/Makefile: make tdump)\n");
+            rc = 2;
+#endif
         }
 
         std::vector<double> s = ms;

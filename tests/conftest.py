@@ -20,7 +20,10 @@ GOLDEN_HASHED = [g for g in _NPZ if g.endswith("h")]
 # "...c" fixtures (config 5 at size) hold row CRC-32s only; the scene comes from
 # the generator inside the harness binaries
 GOLDEN_CRC = [g for g in _NPZ if g.endswith("c")]
-GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h") and not g.endswith("c")]
+# "..._T" fixtures hold the reference's own primary hit distances (dump mode),
+# written by the patched scratch build oracle/Makefile `tdump` makes
+GOLDEN_T = [g for g in _NPZ if g.endswith("_T")]
+GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h") and not g.endswith("c") and not g.endswith("_T")]
 # the 1080p frame is the bench workload; CPU tests use the 800x480 cases
 GOLDEN_SMALL = [g for g in GOLDEN_ALL if "1080p" not in g]
 

@@ -62,3 +62,18 @@ def test_core_primary_hit_distance_matches_oracle(entry, hostsim):
         _, t_want, _ = entry.oracle_render(blob, packet=1, want_t=True)
         _, t_got, _ = run_hostsim(hostsim, blob, want_t=True)
         assert np.array_equal(t_got.view(np.uint32), t_want.view(np.uint32)), name
+
+
+def test_core_primary_hit_distance_matches_reference(entry, hostsim):
+    """... and the reference's own ctx_T_BUF(0) (fixtures "_T": patched scratch
+    build of the reference, oracle/Makefile `tdump`, tracer.cpp:5161)."""
+    from conftest import GOLDEN_T
+    assert GOLDEN_T
+    for name in GOLDEN_T:
+        z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        frame, t_got, _ = run_hostsim(hostsim, z["blob"], want_t=True)
+        want = z["t"]
+        t_got = t_got.reshape(want.shape)
+        assert np.abs(t_got - want).max() <= 1e-5 * np.abs(want).max()
+        assert np.array_equal(t_got.view(np.uint32), want.view(np.uint32)), name
+        assert np.array_equal(frame, z["frame"]), name

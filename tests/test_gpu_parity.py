@@ -7,7 +7,7 @@ distance within 1e-5 relative in dump mode (tolerances written here)."""
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_ALL, GOLDEN_HASHED, GOLDEN_SMALL
+from conftest import GOLDEN_ALL, GOLDEN_HASHED, GOLDEN_SMALL, GOLDEN_T
 
 pytestmark = pytest.mark.gpu
 
@@ -75,6 +75,22 @@ def test_gpu_dump_hits(entry, ctx, name):
     rel = np.abs(t[fin] - want[fin]) / np.abs(want[fin])
     assert rel.max() <= T_REL_TOL
     assert np.array_equal(t.view(np.uint32), want.view(np.uint32))     # in fact identical
+
+
+@pytest.mark.parametrize("name", GOLDEN_T)
+def test_gpu_dump_hits_vs_reference(entry, ctx, name):
+    """Per-sample primary hit distance against the REFERENCE's own ctx_T_BUF(0)
+    (patched scratch build, oracle/Makefile `tdump`, tracer.cpp:5161): within
+    1e-5 relative (north star); in fact bit-identical."""
+    import os
+    z = np.load(os.path.join(entry.GOLDEN_DIR, name + ".npz"))
+    blob, ref, want = z["blob"], z["frame"], z["t"]
+    ctx.upload(blob)
+    t = ctx.dump_hits().reshape(want.shape)
+    rel = np.abs(t - want) / np.abs(want)
+    assert rel.max() <= T_REL_TOL, (name, float(rel.max()))
+    assert np.array_equal(t.view(np.uint32), want.view(np.uint32)), name
+    assert np.array_equal(ctx.render_frame(), ref)
 
 
 def test_gpu_ray_counters(entry, ctx):

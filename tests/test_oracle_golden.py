@@ -7,7 +7,9 @@ images, so frames of the reference itself are the known answers.
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_HASHED, GOLDEN_SMALL
+from conftest import GOLDEN_HASHED, GOLDEN_SMALL, GOLDEN_T
+
+T_REL_TOL = 1e-5                # north star: per-ray hit distance, relative
 
 # emulating the reference's 32-lane packets must reproduce its frame bit for bit
 PACKET32 = ["test01_full", "test05_full", "test12_full", "test15_full", "test16_full",
@@ -37,6 +39,22 @@ def test_oracle_per_sample_semantics_match_reference(entry, name):
         for sh in (0, 8, 16):
             d = np.abs(((got >> sh) & 255).astype(int) - ((ref >> sh) & 255).astype(int))
             assert d.max() <= 1, (name, sh, d.max())
+
+
+@pytest.mark.parametrize("name", GOLDEN_T)
+def test_oracle_hit_distance_is_the_reference_s(entry, name):
+    """Dump mode pinned to the reference: ctx_T_BUF(0) as the reference itself
+    stores it at XX_end (tracer.cpp:5161; patched scratch build, oracle/Makefile
+    `tdump`) against the oracle's, with the reference's packets and per sample."""
+    z = np.load(entry.os.path.join(entry.GOLDEN_DIR, name + ".npz"))
+    blob, ref, want = z["blob"], z["frame"], z["t"]
+    for packet in (32, 1):
+        got, t, _ = entry.oracle_render(blob, packet=packet, want_t=True)
+        assert int((got != ref).sum()) == 0
+        t = t.reshape(want.shape)
+        rel = np.abs(t - want) / np.abs(want)
+        assert rel.max() <= T_REL_TOL, (name, packet, float(rel.max()))
+        assert np.array_equal(t.view(np.uint32), want.view(np.uint32)), (name, packet)   # in fact identical
 
 
 def test_oracle_other_packet_widths_agree(entry):

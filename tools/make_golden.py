@@ -50,6 +50,19 @@ CASES.update({
     # bounding-volume arrays (apps/qr_synth_scene.h), with and without mirrors
     "synth1k_a4":     "-s synth -N 1000 -E 25 -x 480 -y 270 -a 2",
     "synth400_metal": "-s synth -N 400 -E 16 -M 300 -S 7 -x 400 -y 240",
+    # BASELINE.json config 3 as stated: Fresnel (and gamma) props ON, i.e.
+    # RT_OPTS_FRESNEL / RT_OPTS_GAMMA cleared (format.h:59-60, 73-75)
+    "test02_full_rg":   "-s test02 -p full -r -g",
+    "test09_full_rg":   "-s test09 -p full -r -g",
+    "test12_full_rg":   "-s test12 -p full -r -g",
+    "test14_full_rg":   "-s test14 -p full -r -g",
+    "test15_full_a4rg": "-s test15 -p full -a 2 -r -g",
+    "test16_full_a4rg": "-s test16 -p full -a 2 -r -g",
+    "test17_full_rg":   "-s test17 -p full -r -g",
+    "test18_full_a2rg": "-s test18 -p full -a 1 -r -g",
+    "demo01_a4rg":      "-s demo01 -a 2 -r -g",
+    "demo02_a4rg":      "-s demo02 -a 2 -r -g",
+    "demo03_a4rg":      "-s demo03 -a 2 -r -g -b 1000",
 })
 
 
@@ -65,6 +78,18 @@ CASES_HASHED = {
     "test17_1080p_a4h": "-s test17 -p full -x 1920 -y 1080 -a 2",
     "test18_1080p_a4h": "-s test18 -p full -x 1920 -y 1080 -a 2",
     "demo03_4k_a4gh":   "-s demo03 -x 3840 -y 2160 -a 2 -g",
+    # config 3 with the Fresnel + gamma props on, at the stated 1920x1080
+    "test02_1080p_a4rgh": "-s test02 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test09_1080p_a4rgh": "-s test09 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test12_1080p_a4rgh": "-s test12 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test14_1080p_a4rgh": "-s test14 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test15_1080p_a4rgh": "-s test15 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test16_1080p_a4rgh": "-s test16 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test17_1080p_a4rgh": "-s test17 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "test18_1080p_a4rgh": "-s test18 -p full -x 1920 -y 1080 -a 2 -r -g",
+    "demo01_1080p_a4rgh": "-s demo01 -x 1920 -y 1080 -a 2 -r -g",
+    "demo02_1080p_a4rgh": "-s demo02 -x 1920 -y 1080 -a 2 -r -g",
+    "demo03_1080p_a4rgh": "-s demo03 -x 1920 -y 1080 -a 2 -r -g",
 }
 
 
@@ -76,6 +101,42 @@ CASES_CRC = {
     "synth10k_8k_a4c":    "-s synth -N 10000 -x 7680 -y 4320 -a 2",
     "synth100k_1080p_c":  "-s synth -N 100000 -x 1920 -y 1080",
 }
+
+
+# Dump-mode pins ("_T" suffix): primary hit distance per sample written by the
+# reference itself -- oracle/_ref/qr_ref_tdump, the reference with one store
+# added at XX_end in a scratch copy (oracle/Makefile `tdump`, tracer.cpp:5161).
+CASES_T = {
+    "test17_q_a4_T": "-s test17 -p full -x 400 -y 240 -a 2",
+    "test15_q_a2_T": "-s test15 -p full -x 400 -y 240 -a 1",
+    "test14_q_T":    "-s test14 -p full -x 400 -y 240",
+    "synth400_q_T":  "-s synth -N 400 -E 16 -M 300 -S 7 -x 400 -y 240",      # has misses (T stays at the camera's t_max)
+    "test16_q_T":    "-s test16 -p full -x 400 -y 240 -r -g",
+    "demo03_q_a4_T": "-s demo03 -x 400 -y 240 -a 2 -g",
+}
+
+
+def main_t(names):
+    tdump = os.path.join(ROOT, "oracle", "_ref", "qr_ref_tdump")
+    for name in names:
+        args = CASES_T[name].split()
+        with tempfile.TemporaryDirectory() as td:
+            rf, tf, of, bf = (os.path.join(td, n) for n in ("r.raw", "t.raw", "o.raw", "s.blob"))
+            jr = run([tdump] + args + ["-o", rf, "-T", tf])
+            ju = run([REF] + args + ["-o", of])
+            w, h = jr["x_res"], jr["y_res"]
+            frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
+            # the added store does not change the frame the reference renders
+            assert np.array_equal(frame, np.fromfile(of, dtype=np.uint32).reshape(h, w)), name
+            t = np.fromfile(tf, dtype=np.float32).reshape(h, w << jr["fsaa"])
+            run([ORC] + args + ["-o", of], {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_ROWS": "1"})
+            blob = np.fromfile(bf, dtype=np.uint8)
+        meta = {"name": name, "args": CASES_T[name], "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
+                "opts": jr["opts"], "ref_simd": jr["simd"], "hit_fraction": float(np.isfinite(t).mean())}
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, blob=blob, frame=frame, t=t,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print("%-20s %4dx%-4d hit %.3f  npz %7d B" % (name, w, h, meta["hit_fraction"], os.path.getsize(path)))
 
 
 def main_crc(names):
@@ -179,7 +240,8 @@ def main(names):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED) + list(CASES_CRC))
+    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED) + list(CASES_CRC) + list(CASES_T))
     main([n for n in names if n in CASES])
     main_hashed([n for n in names if n in CASES_HASHED])
     main_crc([n for n in names if n in CASES_CRC])
+    main_t([n for n in names if n in CASES_T])
