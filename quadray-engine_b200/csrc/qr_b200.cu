@@ -46,7 +46,8 @@ static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {38
                                      {896, 1}, {1024, 1} };
 #define QR_N_SHAPES     8
 #define QR_DEFAULT_SHAPE 2
-#define QR_BIG_SHAPE     7          /* 1024 threads at 64 registers */
+#define QR_BIG_SHAPE     3          /* 768 threads at 80 registers: 24 warps per SM and few spills
+                                       (1024 x 64 spills p_obj into the walk, 640 x 96 has 20 warps) */
 #define QR_BIG_FRAME_ITEMS 60000    /* work items (32 samples each) per GPU from which QR_BIG_SHAPE pays */
 
 /* ------------------------------------------------------------------ PTX --- */
@@ -191,9 +192,10 @@ qr_render_kernel(const qr_launch p)
     qr_scratch sc;
     sc.addr = smem_u32(qr_smem) + p.stage_bytes + threadIdx.x * 16u;
     sc.stride = THREADS * 16u;
-    /* opaque to the optimiser: one register, instead of the address being
-     * recomputed from the thread index at every use */
-    asm volatile("mov.u32 %0, %0;" : "+r"(sc.addr));
+    /* opaque to the optimiser (a volatile round trip through its own scratch):
+     * one register, instead of S2R + LEA from the thread index at every use */
+    asm volatile("st.volatile.shared.b32 [%0], %0;\n\t"
+                 "ld.volatile.shared.b32 %0, [%0];" : "+r"(sc.addr) :: "memory");
     qr_sc_st(sc, QR_SC_MISC, 0.0f, 0.0f, 0.0f, 0.0f);
 
     /* one work item = one packet (a 4 x bh pixel block of a tile); the queue
@@ -696,7 +698,30 @@ static int qr_grow(qr_ctx *ctx, void **ptr, size_t *cap, size_t need, bool pinne
     }
     else
     {
-        QR_CUDA(ctx, cudaMalloc(ptr, n));
+        /* The walk's element cursor is ONE 32-bit word (qr_core.cuh, qr_ecur):
+         * no device buffer may straddle a 4 GB boundary.  cudaMalloc hardly
+         * ever returns one that does; if so, allocate again while it is held. */
+        void *held[4] = { NULL, NULL, NULL, NULL };
+        int nheld = 0;
+        cudaError_t err = cudaSuccess;
+        for (;;)
+        {
+            err = cudaMalloc(ptr, n);
+            if (err != cudaSuccess) break;
+            const unsigned long long a = (unsigned long long)*ptr;
+            if ((a >> 32) == ((a + n - 1) >> 32)) break;
+            if (nheld == 4 || n >= (1ull << 32))
+            {
+                cudaFree(*ptr);
+                *ptr = NULL;
+                err = cudaErrorMemoryAllocation;
+                break;
+            }
+            held[nheld++] = *ptr;
+            *ptr = NULL;
+        }
+        for (int i = 0; i < nheld; i++) cudaFree(held[i]);
+        QR_CUDA(ctx, err);
     }
     *cap = n;
     return QR_OK;

@@ -181,7 +181,10 @@ template <> struct qr_hot<true>
 #define QR_SC_MISC   5
 #define QR_SC_WORG   6      /* world origin / direction of the ray being walked: parked for */
 #define QR_SC_WRAY   7      /* the walk, which transforms its copy in place inside nodes */
-#define QR_SC_QUADS  8
+#define QR_SC_NORG   8      /* the ray in the space of the node being opened: written and read */
+#define QR_SC_NRAY   9      /* straight back, so that the walk's ray registers are (re)defined by
+                               loads only and no copies of them are carried around the loop */
+#define QR_SC_QUADS  10
 
 #if defined(__CUDACC__)
 /* (the host pass of nvcc parses these too; it never calls them) */
@@ -528,8 +531,8 @@ QR_HD_COLD bool qr_clip_custom(const typename qr_hot<SH>::base_t surf, const qr_
  * surface's field set (world or trnode space).  On success lx/ly/lz hold the
  * (possibly adjusted) local hit point.
  */
-template <bool SH>
-QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0,
+template <bool SH, typename V>
+QR_HD bool qr_clip(const V &v, uint32_t so, uint32_t d, const qr_f4 q0,
                    const qr_scratch sc, bool xf, float bo0, float bo1, float bo2,
                    float lr0, float lr1, float lr2, float ld0, float ld1, float ld2,
                    float t, bool dmask, uint32_t amask, int side,
@@ -537,13 +540,8 @@ QR_HD bool qr_clip(const qr_view<SH> &v, uint32_t so, uint32_t d, const qr_f4 q0
 {
     /* the world ray: the current frame itself, or parked in the scratch while
      * the walk is inside a transform node / a surface's own matrix */
-    float ox = bo0, oy = bo1, oz = bo2, rx = lr0, ry = lr1, rz = lr2;
-    if (xf)
-    {
-        const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
-        ox = wo.x; oy = wo.y; oz = wo.z;
-        rx = wr.x; ry = wr.y; rz = wr.z;
-    }
+    const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
+    const float ox = wo.x, oy = wo.y, oz = wo.z, rx = wr.x, ry = wr.y, rz = wr.z;
     const float hx = qr_add(qr_mul(rx, t), ox);
     const float hy = qr_add(qr_mul(ry, t), oy);
     const float hz = qr_add(qr_mul(rz, t), oz);
@@ -603,10 +601,91 @@ QR_HD uint32_t qr_side_props(uint32_t packed, int side)
 }
 
 /*
- * One list walk, OO_cyc 1341 .. OO_out 5142, for one sample.
- *   mode CLOSEST: returns true when something was hit; t_buf and the scratch
- *                 quad QR_SC_BEST (surface | side, local hit) are updated
- *   mode SHADOW : returns true when the sample is in shadow (first occluder)
+ * Cursor into the element array.  On the device the array never straddles a
+ * 4 GB boundary (qr_scene_upload sees to that), so the upper address word is a
+ * constant and stepping / skipping is ONE 32-bit add on the lower word.
+ */
+#if defined(__CUDA_ARCH__)
+struct qr_ecur { unsigned long long p; };
+QR_HD qr_ecur qr_e_at(const qr_kelem *base, uint32_t idx)
+{
+    qr_ecur c;
+    c.p = (unsigned long long)(base + idx);
+    return c;
+}
+QR_HD qr_kelem qr_e_ld(const qr_ecur c)
+{
+    qr_kelem e;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(e.w), "=r"(e.aux) : "l"(c.p));
+    return e;
+}
+QR_HD void qr_e_skip(qr_ecur &c, int32_t bytes)
+{
+    /* 32-bit add on the lower word of the 64-bit register pair */
+    asm("{\n\t.reg .b32 lo, hi;\n\t"
+        "mov.b64 {lo, hi}, %0;\n\t"
+        "add.u32 lo, lo, %1;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(c.p) : "r"(bytes));
+}
+#else
+struct qr_ecur { const uint8_t *p; };
+QR_HD qr_ecur qr_e_at(const qr_kelem *base, uint32_t idx) { qr_ecur c; c.p = (const uint8_t *)(base + idx); return c; }
+QR_HD qr_kelem qr_e_ld(const qr_ecur c) { return *(const qr_kelem *)c.p; }
+QR_HD void qr_e_skip(qr_ecur &c, int32_t bytes) { c.p += bytes; }
+#endif
+
+/*
+ * One candidate root "t" of the surface at "so" on "side": depth tests
+ * (CC_clp 1602-1610), clipping, then the hit is taken.  Returns true when the
+ * surface is done (hit taken, or a shadow walk met a transparent occluder).
+ *   closest walk: t_buf = t, best-hit record into the scratch
+ *   shadow walk : an occluder sets t_buf = -inf and parks the cursor in front
+ *                 of element 0 (an END), so the walk ends at its next step
+ */
+template <bool SH, typename V>
+QR_HD bool qr_candidate(const V &v, const qr_scratch sc, uint32_t w, uint32_t so, int mode,
+                        float bo0, float bo1, float bo2, float cr0, float cr1, float cr2,
+                        float ld0, float ld1, float ld2, bool have_ld,
+                        float t, bool dmask, uint32_t amask, int side,
+                        float t_min, float &t_buf, qr_ecur &cur)
+{
+    if (!qr_gt(t_buf, t)) return false;
+    if (!(t_min < t)) return false;
+
+    /* the record's first quad is read here rather than kept alive through
+     * the solver */
+    const qr_f4 q0 = QR_SURF(v, so, 0);
+    const uint32_t d = qr_f2u(q0.w);
+    if (!have_ld && (d & QR_D_TRM_MASK))
+    {
+        /* planes X / Y / Z solve with one coordinate; inside a node the
+         * clipper wants the whole local origin */
+        ld0 = qr_sub(bo0, q0.x); ld1 = qr_sub(bo1, q0.y); ld2 = qr_sub(bo2, q0.z);
+    }
+    float lx, ly, lz;
+    if (!qr_clip<SH>(v, so, d, q0, sc, (w & QR_KF_NODE) != 0, bo0, bo1, bo2, cr0, cr1, cr2,
+                     ld0, ld1, ld2, t, dmask, amask, side, lx, ly, lz)) return false;
+    if (mode == QR_MODE_SHADOW)
+    {
+        if (qr_casts_shadow(qr_side_props(qr_f2u(QR_SURF(v, so, 2).w), side)))
+        {
+            t_buf = qr_u2f(0xFF800000u);
+            cur = qr_e_at(v.elems, 0);
+            qr_e_skip(cur, -(int32_t)sizeof(qr_kelem));
+        }
+        return true;
+    }
+    t_buf = t;
+    qr_sc_st(sc, QR_SC_BEST, qr_u2f(so | (uint32_t)side), lx, ly, lz);
+    return true;
+}
+
+/*
+ * One list walk, OO_cyc 1341 .. OO_out 5142, for one sample.  Returns t_buf:
+ *   mode CLOSEST: below the t_max it started from when something was hit; the
+ *                 scratch quad QR_SC_BEST (surface | side, local hit) is set
+ *   mode SHADOW : -inf when the sample is in shadow (first occluder)
  * The scratch quad QR_SC_LOC holds the stored local hit of the originating
  * level (NRM_I/J/K of the previous context), used when the ray starts on the
  * surface tested (p_obj, tracer.cpp:1352-1373).
@@ -615,188 +694,176 @@ QR_HD uint32_t qr_side_props(uint32_t packed, int side)
  * or the space of the open transform node (transform caching, tracer.cpp:
  * 1377-1421, 1483-1500), or for one element the space of a surface with its
  * own matrix.  Which elements open / close a frame is compiled into the
- * element flags (qr_kscene.h).  Elements are sequential, so the successor is
- * loaded while the current one is processed; a bounding-volume element also
- * loads its skip target up front.
+ * element stream (qr_kscene.h); the world ray waits in the scratch meanwhile.
+ *
+ * The loop is written for a small instruction count per element: kinds are
+ * tested most frequent first, nothing but the ray, t_buf and the cursor lives
+ * across an iteration, the cursor is one 32-bit word, and the next element is
+ * loaded where it is known (the other warps of the SM hide the latency).
  */
+#if defined(__CUDACC__) && defined(QR_WALK_NOINLINE)
+#define QR_WALK_FN __device__ __noinline__
+#else
+#define QR_WALK_FN QR_HD
+#endif
 template <bool SH>
-QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
+QR_WALK_FN float qr_walk(const typename qr_hot<SH>::base_t surf, const qr_kelem *elems, uint32_t head, int mode,
                    float ox, float oy, float oz, float rx, float ry, float rz,
                    float t_min, float t_max, uint32_t p_obj, int p_flg,
-                   const qr_scratch sc, float &t_buf)
+                   const qr_scratch sc)
 {
-    /* (bo, cr): origin and direction in the current frame, transformed IN
-     * PLACE; the world ray waits in the scratch (xf: current frame != world) */
+    struct { typename qr_hot<SH>::base_t surf; const qr_kelem *elems; } v = { surf, elems };
     qr_sc_st(sc, QR_SC_WORG, ox, oy, oz, 0.0f);
     qr_sc_st(sc, QR_SC_WRAY, rx, ry, rz, 0.0f);
     float bo0 = ox, bo1 = oy, bo2 = oz;
     float cr0 = rx, cr1 = ry, cr2 = rz;
-    bool  xf = false;
     const int  pf = p_flg & (QR_FLAG_SIDE | QR_FLAG_PASS);
     /* a root t <= 0 (or NaN) can never pass t_min < t when t_min >= 0 */
     const bool no_neg = !(t_min < 0.0f);
+    float t_buf = t_max;
 
-    t_buf = t_max;
-
-    uint32_t ei = head;
-    qr_kelem e = v.elems[ei];
+    qr_ecur cur = qr_e_at(v.elems, head);
+    qr_kelem e = qr_e_ld(cur);
 
     for (;;)
     {
         const uint32_t w = e.w;
         const uint32_t kind = QR_K_KIND(w);
-        uint32_t ni = ei + 1;
-        qr_kelem en = v.elems[ni];              /* successor, in flight during this element
-                                                   (the array ends with a spare END) */
-        if (kind > QR_K_TWOPLANE)
+        const uint32_t so = QR_K_SURF_OFF(w);
+
+        if (kind == QR_K_BV)
         {
-            /* the rare kinds */
-            if (kind == QR_K_END) break;
-            if (kind == QR_K_JUMP)
-            {
-                ni = (uint32_t)e.aux;
-                en = v.elems[ni];
-            }
-            else
-            if (kind == QR_K_OPEN)
-            {
-                /* array with a matrix: transform origin diff and ray once for
-                 * the elements up to the node's last one (1483-1496) */
-                const uint32_t so = QR_K_SURF_OFF(w);
-                const qr_f4 q0 = QR_SURF(v, so, 0);
-                const qr_f4 q5 = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
-                const float tckz = QR_SURF(v, so, 7).x;
-                const uint32_t trm = QR_D_TRM(qr_f2u(q0.w));
-                if (xf)
-                {
-                    /* nodes do not nest (the element compiler closes one before
-                     * it opens the next); should one ever, start from the world */
-                    const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
-                    bo0 = wo.x; bo1 = wo.y; bo2 = wo.z;
-                    cr0 = wr.x; cr1 = wr.y; cr2 = wr.z;
-                }
-                qr_xform(q5, q6, tckz, trm, qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
-                         bo0, bo1, bo2);
-                qr_xform(q5, q6, tckz, trm, cr0, cr1, cr2, cr0, cr1, cr2);
-                xf = true;
-            }
-            ei = ni;
-            e = en;
+            /* AR_ptr 3955-4054: bounding volume of an array */
+            const qr_f4 q0 = QR_SURF(v, so, 0);
+            const qr_f4 q1 = QR_SURF(v, so, 1);
+            const float ld0 = qr_sub(bo0, q0.x), ld1 = qr_sub(bo1, q0.y), ld2 = qr_sub(bo2, q0.z);
+            float x1 = cr0;
+            float x0 = qr_mul(q1.x, x1);
+            float x5 = ld0;
+            float q7 = qr_mul(q1.x, x5);
+            float x3 = x1;
+            x1 = qr_mul(x1, x0); x3 = qr_mul(x3, q7); x5 = qr_mul(x5, q7);
+
+            float x2 = cr1;
+            x0 = qr_mul(q1.y, x2);
+            float x6 = ld1;
+            q7 = qr_mul(q1.y, x6);
+            float x4 = x2;
+            x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
+            x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
+
+            x2 = cr2;
+            x0 = qr_mul(q1.z, x2);
+            x6 = ld2;
+            q7 = qr_mul(q1.z, x6);
+            x4 = x2;
+            x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
+            x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
+
+            x5 = qr_sub(x5, q1.w);
+            x5 = qr_mul(x5, x1);
+            x3 = qr_mul(x3, x3);
+            x3 = qr_sub(x3, x5);
+            /* AR_skp: on a miss continue behind the array's last leaf */
+            const bool miss = !(0.0f <= x3);
+            qr_e_skip(cur, miss ? e.aux : (int32_t)sizeof(qr_kelem));
+            e = qr_e_ld(cur);
             continue;
         }
 
-        bool reset = (w & (QR_KF_CLOSE | QR_KF_OWNTRM)) != 0;
-
-        do
+        if (kind <= QR_K_PLANE_G)
         {
-            const uint32_t so = QR_K_SURF_OFF(w);
-            const qr_f4 q0 = QR_SURF(v, so, 0);
-            const uint32_t d = qr_f2u(q0.w);
-
-            if (kind == QR_K_BV)
-            {
-                /* AR_ptr 3955-4054: bounding volume of an array */
-                const qr_kelem ea = v.elems[(uint32_t)e.aux];
-                const qr_f4 q1 = QR_SURF(v, so, 1);
-                const float ld0 = qr_sub(bo0, q0.x), ld1 = qr_sub(bo1, q0.y), ld2 = qr_sub(bo2, q0.z);
-                float x1 = cr0;
-                float x0 = qr_mul(q1.x, x1);
-                float x5 = ld0;
-                float q7 = qr_mul(q1.x, x5);
-                float x3 = x1;
-                x1 = qr_mul(x1, x0); x3 = qr_mul(x3, q7); x5 = qr_mul(x5, q7);
-
-                float x2 = cr1;
-                x0 = qr_mul(q1.y, x2);
-                float x6 = ld1;
-                q7 = qr_mul(q1.y, x6);
-                float x4 = x2;
-                x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
-                x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
-
-                x2 = cr2;
-                x0 = qr_mul(q1.z, x2);
-                x6 = ld2;
-                q7 = qr_mul(q1.z, x6);
-                x4 = x2;
-                x2 = qr_mul(x2, x0); x4 = qr_mul(x4, q7); x6 = qr_mul(x6, q7);
-                x1 = qr_add(x1, x2); x3 = qr_add(x3, x4); x5 = qr_add(x5, x6);
-
-                x5 = qr_sub(x5, q1.w);
-                x5 = qr_mul(x5, x1);
-                x3 = qr_mul(x3, x3);
-                x3 = qr_sub(x3, x5);
-                /* AR_skp: on a miss continue behind the array's last leaf
-                 * (selects, not a branch: this is the hottest decision) */
-                const bool miss = !(0.0f <= x3);
-                ni = miss ? (uint32_t)e.aux : ni;
-                en.w = miss ? ea.w : en.w;
-                en.aux = miss ? ea.aux : en.aux;
-                reset = miss && (w & QR_KF_SKIPCLOSE) != 0;
-                break;
-            }
-
+            /* the leaves */
             const bool same = (so == p_obj);
-            float ld0, ld1, ld2;
-
-            if (w & QR_KF_OWNTRM)
+            do
             {
-                /* OO_dff 1429-1556: surface with its own matrix */
-                const qr_f4 q5t = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
-                const float tckz = QR_SURF(v, so, 7).x;
-                if (!same)
+                if (kind <= QR_K_PLANE_Z)
                 {
-                    qr_xform(q5t, q6, tckz, QR_D_TRM(d), qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
-                             ld0, ld1, ld2);
+                    /* PL_ptr 4062-4136; the element carries the axis K,
+                     * a_sgn[K] and pos[K].  The reference divides
+                     * (d ^ s ^ sign) by (r ^ s), s = a_sgn[K]: the quotient
+                     * and the sign test do not depend on s, the side does */
+                    if (same) break;
+                    const bool px = kind == QR_K_PLANE_X, py = kind == QR_K_PLANE_Y;
+                    const float ok = px ? bo0 : (py ? bo1 : bo2);
+                    const float rk = px ? cr0 : (py ? cr1 : cr2);
+                    const float dk = qr_sub(ok, qr_u2f((uint32_t)e.aux));
+                    if (!(0.0f != rk)) break;
+                    if (no_neg && (int32_t)(qr_f2u(dk) ^ qr_f2u(rk)) >= 0) break;
+                    const float t = qr_div(qr_neg(dk), rk);
+                    const uint32_t sg = (w << (31 - 6)) & 0x80000000u;  /* QR_KF_SGN -> sign bit */
+                    const int side = (qr_u2f(qr_f2u(rk) ^ sg) < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
+                    qr_candidate<SH>(v, sc, w, so, mode, bo0, bo1, bo2, cr0, cr1, cr2, 0.0f, 0.0f, 0.0f, false,
+                                     t, false, 0u, side, t_min, t_buf, cur);
+                    break;
                 }
-                qr_xform(q5t, q6, tckz, QR_D_TRM(d), cr0, cr1, cr2, cr0, cr1, cr2);
-                xf = true;
-            }
-            else
-            {
-                ld0 = qr_sub(bo0, q0.x);
-                ld1 = qr_sub(bo1, q0.y);
-                ld2 = qr_sub(bo2, q0.z);
-            }
-            if (same)
-            {
-                /* 1352-1373: secondary ray leaving this very surface reuses the
-                 * stored local hit as its local diff */
-                const qr_f4 pl = qr_sc_ld(sc, QR_SC_LOC);
-                ld0 = pl.x; ld1 = pl.y; ld2 = pl.z;
-            }
 
-            /* candidate roots, tried in the order (first, first ^ 1) */
-            float t1n, t1d, t2n, t2d;           /* lazily divided roots (outer, inner) */
-            float t1 = 0.0f, t2 = 0.0f;         /* roots when "ready" */
-            bool  k1 = true, k2 = true, ready, dmask = false;
-            uint32_t amask = 0;
-            int   first, npass;
+                float ld0, ld1, ld2;
+                const qr_f4 q0 = QR_SURF(v, so, 0);
+                if (same || (w & QR_KF_OWN))
+                {
+                    /* the rarer prologues */
+                    ld0 = ld1 = ld2 = 0.0f;
+                    if (w & QR_KF_OWN)
+                    {
+                        /* OO_dff 1429-1556: surface with its own matrix */
+                        const qr_f4 q5t = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
+                        const float tckz = QR_SURF(v, so, 7).x;
+                        const uint32_t trm = QR_D_TRM(qr_f2u(q0.w));
+                        if (!same)
+                        {
+                            qr_xform(q5t, q6, tckz, trm, qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
+                                     ld0, ld1, ld2);
+                        }
+                        float n0, n1, n2;
+                        qr_xform(q5t, q6, tckz, trm, cr0, cr1, cr2, n0, n1, n2);
+                        qr_sc_st(sc, QR_SC_NRAY, n0, n1, n2, 0.0f);
+                        const qr_f4 nr = qr_sc_ld(sc, QR_SC_NRAY);
+                        cr0 = nr.x; cr1 = nr.y; cr2 = nr.z;
+                    }
+                    else
+                    {
+                        ld0 = qr_sub(bo0, q0.x); ld1 = qr_sub(bo1, q0.y); ld2 = qr_sub(bo2, q0.z);
+                    }
+                    if (same)
+                    {
+                        /* 1352-1373: secondary ray leaving this very surface
+                         * reuses the stored local hit as its local diff */
+                        const qr_f4 pl = qr_sc_ld(sc, QR_SC_LOC);
+                        ld0 = pl.x; ld1 = pl.y; ld2 = pl.z;
+                    }
+                    if (kind == QR_K_PLANE_G)
+                    {
+                        /* PL_ptr with the axis map and sign of the descriptor */
+                        if (same) break;
+                        const uint32_t d = qr_f2u(q0.w);
+                        const uint32_t k = QR_D_MAP(d, 2);
+                        const uint32_t sg = (d << (31 - 14)) & 0x80000000u;     /* a_sgn[K] */
+                        const float dk = qr_pick3(k, ld0, ld1, ld2);
+                        const float rk = qr_pick3(k, cr0, cr1, cr2);
+                        if (!(0.0f != rk)) break;
+                        if (no_neg && (int32_t)(qr_f2u(dk) ^ qr_f2u(rk)) >= 0) break;
+                        const float t = qr_div(qr_neg(dk), rk);
+                        const int side = (qr_u2f(qr_f2u(rk) ^ sg) < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
+                        qr_candidate<SH>(v, sc, w, so, mode, bo0, bo1, bo2, cr0, cr1, cr2, ld0, ld1, ld2, true,
+                                         t, false, 0u, side, t_min, t_buf, cur);
+                        break;
+                    }
+                }
+                else
+                {
+                    ld0 = qr_sub(bo0, q0.x);
+                    ld1 = qr_sub(bo1, q0.y);
+                    ld2 = qr_sub(bo2, q0.z);
+                }
 
-            if (kind == QR_K_PLANE)
-            {
-                /* PL_ptr 4062-4136 */
-                if (same) break;
-                const uint32_t k = QR_D_MAP(d, 2);
-                const uint32_t sg = (d << (31 - 14)) & 0x80000000u;     /* a_sgn[K] */
-                const uint32_t dk = (qr_f2u(qr_pick3(k, ld0, ld1, ld2)) ^ sg) ^ 0x80000000u;
-                const uint32_t rk = qr_f2u(qr_pick3(k, cr0, cr1, cr2)) ^ sg;
-                if (!(0.0f != qr_u2f(rk))) break;
-                if (no_neg && (int32_t)(dk ^ rk) < 0) break;
-                t1 = t2 = qr_div(qr_u2f(dk), qr_u2f(rk));
-                first = (qr_u2f(rk) < 0.0f) ? QR_FLAG_SIDE_OUTER : QR_FLAG_SIDE_INNER;
-                npass = 1;
-                ready = true;
-                t1n = t1d = t2n = t2d = 0.0f;
-            }
-            else
-            {
                 float a_val, b_val, c_val, d_val;
                 const qr_f4 q1 = QR_SURF(v, so, 1);
 
                 if (kind == QR_K_TWOPLANE)
                 {
                     /* TP_ptr 4216-4277 */
+                    const uint32_t d = qr_f2u(q0.w);
                     const uint32_t iI = QR_D_MAP(d, 0), iK = QR_D_MAP(d, 2);
                     const float sci_i = qr_pick3(iI, q1.x, q1.y, q1.z), sci_k = qr_pick3(iK, q1.x, q1.y, q1.z);
                     const float ri = qr_pick3(iI, cr0, cr1, cr2), di = qr_pick3(iI, ld0, ld1, ld2);
@@ -847,16 +914,17 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
                 if (!(0.0f <= d_val)) break;
                 const qr_f4 q7 = QR_SURF(v, so, 7);
                 const float b = qr_neg(b_val);
-                dmask = d_val < q7.y;
+                const bool dmask = d_val < q7.y;
                 const float sd = qr_u2f(qr_f2u(qr_sqrt(d_val)) ^ (qr_f2u(b) & 0x80000000u));
                 const float bd = qr_add(b, sd);
                 const bool m_pos = 0.0f <= sd;
-                t1n = m_pos ? c_val : bd;
-                t1d = m_pos ? bd : a_val;
-                t2n = m_pos ? bd : c_val;
-                t2d = m_pos ? a_val : bd;
-                amask = qr_f2u(a_val) & 0x80000000u;
-                ready = dmask;
+                float t1n = m_pos ? c_val : bd;     /* lazily divided roots (outer, inner) */
+                float t1d = m_pos ? bd : a_val;
+                float t2n = m_pos ? bd : c_val;
+                float t2d = m_pos ? a_val : bd;
+                const uint32_t amask = qr_f2u(a_val) & 0x80000000u;
+                float t1 = 0.0f, t2 = 0.0f;         /* the roots when dmask */
+                bool  k1 = true, k2 = true;
 
                 if (dmask)
                 {
@@ -880,65 +948,81 @@ QR_HD bool qr_walk(const qr_view<SH> &v, uint32_t head, int mode,
 
                 /* QD_srt 4646-4824, one lane: the side tried first follows the
                  * sign of "a"; a hit on the first side ends the surface */
-                first = qr_gt(0.0f, a_val) ? QR_FLAG_SIDE_INNER : QR_FLAG_SIDE_OUTER;
-                npass = 2;
-            }
+                const int first = qr_gt(0.0f, a_val) ? QR_FLAG_SIDE_INNER : QR_FLAG_SIDE_OUTER;
 
 #pragma unroll 1
-            for (int pass = 0; pass < npass; pass++)
-            {
-                const int side = first ^ pass;
-                /* CHECK_SIDE 531-540 */
-                if (same && (pf == 1 - side || pf == 2 + side)) continue;
-                float t; bool k;
-                if (ready)
+                for (int pass = 0; pass < 2; pass++)
                 {
-                    t = side == QR_FLAG_SIDE_OUTER ? t1 : t2;
-                    k = side == QR_FLAG_SIDE_OUTER ? k1 : k2;
+                    const int side = first ^ pass;
+                    /* CHECK_SIDE 531-540 */
+                    if (same && (pf == 1 - side || pf == 2 + side)) continue;
+                    const bool outer = side == QR_FLAG_SIDE_OUTER;
+                    float t; bool k;
+                    if (dmask)
+                    {
+                        t = outer ? t1 : t2;
+                        k = outer ? k1 : k2;
+                    }
+                    else
+                    {
+                        const float nn = outer ? t1n : t2n;
+                        const float dd = outer ? t1d : t2d;
+                        /* a quotient with the sign bit set cannot pass t_min < t */
+                        if (no_neg && (int32_t)(qr_f2u(nn) ^ qr_f2u(dd)) < 0) continue;
+                        t = qr_div(nn, dd);
+                        k = dd != 0.0f;
+                    }
+                    if (!k) continue;
+                    if (qr_candidate<SH>(v, sc, w, so, mode, bo0, bo1, bo2, cr0, cr1, cr2, ld0, ld1, ld2, true,
+                                         t, dmask, amask, side, t_min, t_buf, cur)) break;
                 }
-                else
-                {
-                    const float nn = side == QR_FLAG_SIDE_OUTER ? t1n : t2n;
-                    const float dd = side == QR_FLAG_SIDE_OUTER ? t1d : t2d;
-                    t = qr_div(nn, dd);
-                    k = dd != 0.0f;
-                }
-                if (!k) continue;
-                /* CC_clp 1602-1610: depth tests */
-                if (!qr_gt(t_buf, t)) continue;
-                if (!(t_min < t)) continue;
-                float lx, ly, lz;
-                if (!qr_clip<SH>(v, so, d, q0, sc, xf, bo0, bo1, bo2, cr0, cr1, cr2, ld0, ld1, ld2,
-                                 t, dmask, amask, side, lx, ly, lz)) continue;
-                if (mode == QR_MODE_SHADOW)
-                {
-                    if (qr_casts_shadow(qr_side_props(qr_f2u(QR_SURF(v, so, 2).w), side))) return true;
-                    break;
-                }
-                t_buf = t;
-                qr_sc_st(sc, QR_SC_BEST, qr_u2f(so | (uint32_t)side), lx, ly, lz);
-                break;
             }
-        }
-        while (0);
+            while (0);
 
-        /* after the last element of the open transform node / an own matrix:
-         * back to the world */
-        if (reset)
-        {
-            const qr_f4 wo = qr_sc_ld(sc, QR_SC_WORG), wr = qr_sc_ld(sc, QR_SC_WRAY);
-            bo0 = wo.x; bo1 = wo.y; bo2 = wo.z;
-            cr0 = wr.x; cr1 = wr.y; cr2 = wr.z;
-            xf = false;
+            qr_e_skip(cur, (int32_t)sizeof(qr_kelem));
+            e = qr_e_ld(cur);
+            continue;
         }
-        ei = ni;
-        e = en;
+
+        /* the rare kinds */
+        if (kind == QR_K_END) break;
+        if (kind == QR_K_OPEN)
+        {
+            /* array with a matrix: transform origin diff and ray once for the
+             * elements up to the node's last one (1483-1496) */
+            const qr_f4 q0 = QR_SURF(v, so, 0);
+            const qr_f4 q5 = QR_SURF(v, so, 5), q6 = QR_SURF(v, so, 6);
+            const float tckz = QR_SURF(v, so, 7).x;
+            const uint32_t trm = QR_D_TRM(qr_f2u(q0.w));
+            float n0, n1, n2;
+            qr_xform(q5, q6, tckz, trm, qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
+                     n0, n1, n2);
+            qr_sc_st(sc, QR_SC_NORG, n0, n1, n2, 0.0f);
+            qr_xform(q5, q6, tckz, trm, cr0, cr1, cr2, n0, n1, n2);
+            qr_sc_st(sc, QR_SC_NRAY, n0, n1, n2, 0.0f);
+            const qr_f4 no = qr_sc_ld(sc, QR_SC_NORG), nr = qr_sc_ld(sc, QR_SC_NRAY);
+            bo0 = no.x; bo1 = no.y; bo2 = no.z;
+            cr0 = nr.x; cr1 = nr.y; cr2 = nr.z;
+        }
+        else
+        if (kind == QR_K_CLOSE)
+        {
+            /* behind the last element of the open transform node / an own
+             * matrix: back to the world (word loads, straight into the
+             * ray's registers) */
+            bo0 = qr_u2f(qr_sc_ld1(sc, QR_SC_WORG, 0)); bo1 = qr_u2f(qr_sc_ld1(sc, QR_SC_WORG, 1));
+            bo2 = qr_u2f(qr_sc_ld1(sc, QR_SC_WORG, 2));
+            cr0 = qr_u2f(qr_sc_ld1(sc, QR_SC_WRAY, 0)); cr1 = qr_u2f(qr_sc_ld1(sc, QR_SC_WRAY, 1));
+            cr2 = qr_u2f(qr_sc_ld1(sc, QR_SC_WRAY, 2));
+        }
+        qr_e_skip(cur, kind == QR_K_JUMP ? e.aux : (int32_t)sizeof(qr_kelem));
+        e = qr_e_ld(cur);
     }
 
-    /* a hit lowered t_buf below the t_max the walk started from (the depth
-     * test is strict, 1602-1605), and a closest-hit walk always starts from
-     * the camera's: no flag to carry through the loop */
-    return mode == QR_MODE_SHADOW ? false : t_buf < v.h->cam_t_max;
+    /* a closest-hit walk lowered t_buf below the t_max it started from when
+     * something was hit (the depth test is strict, 1602-1605); a shadow walk
+     * marks an occluder with t_buf = -inf */
+    return t_buf;
 }
 
 /* texel -> linear colour, PAINT_COLX 664-673 */
@@ -1076,9 +1160,9 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
     for (;;)
     {
         /* ---------------- WALK ---------------- */
-        float t_buf;
-        const bool res = qr_walk<SH>(v, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
-                                     p_obj, p_flg, sc, t_buf);
+        const float t_buf = qr_walk<SH>(v.surf, v.elems, head, mode, ox, oy, oz, rx, ry, rz, t_min, t_max,
+                                        p_obj, p_flg, sc);
+        const bool res = mode == QR_MODE_SHADOW ? t_buf < 0.0f : t_buf < h.cam_t_max;
         {
             /* the ray comes back from where the walk parked it, so it does not
              * occupy registers during the walk */

@@ -52,10 +52,25 @@ struct alignas(16) qr_f4 { float x, y, z, w; };
  * The reference tracks, while it walks a surface list, whether a transform
  * node is open (ctx_LOCAL(OBJ), tracer.cpp:1377-1421, 1492-1496, 4047-4053);
  * that state only depends on the list, not on the ray, so it is resolved
- * here, once per upload, into the element's kind / flag bits:
- *   surface lists  w = surface << 7 | flags | kind,  aux = element to continue
- *                  at when a bounding volume is missed (successor of the
- *                  array's last leaf) or the JUMP target
+ * here, once per upload, into the element stream itself:
+ *   - an array with a matrix becomes an OPEN element (transform the ray into
+ *     the node's space, tracer.cpp:1483-1496); the node's last element is
+ *     followed by a CLOSE element (back to the world ray), which is also
+ *     where a bounding volume INSIDE the node that ends with the node lands
+ *     when it is missed (tracer.cpp:4047-4053);
+ *   - a surface with its own matrix outside any node (OO_dff, 1429-1556)
+ *     carries OWN (the walk transforms the ray for this one element) and is
+ *     followed by a CLOSE as well;
+ *   - every element inside a node (or OWN) carries the NODE flag: the world
+ *     ray is parked in the thread's scratch (qr_core.cuh);
+ *   - a plane's solver only needs ONE coordinate of its position and the
+ *     axis: the axis is part of the kind, the coordinate sits in aux, so a
+ *     plane that is missed costs no access to its surface record at all;
+ *   - aux of a bounding volume / a JUMP is the distance in BYTES from the
+ *     element itself to the slot to continue at (a missed volume: the slot
+ *     behind its array's last leaf in this list, tracer.cpp:4042-4054).
+ *
+ *   surface lists  w = surface << 7 | flags | kind
  *   light lists    w = light, aux = head of the light's shadow list
  *   clip lists     w = clipper surface << 7 | QR_KC_* bits,
  *                  aux = trnode's last element (array clippers)
@@ -66,21 +81,26 @@ struct __align__(8) qr_kelem { uint32_t w; int32_t aux; };
 struct alignas(8) qr_kelem { uint32_t w; int32_t aux; };
 #endif
 
-#define QR_KEND         0xFFFFFFFFu     /* END element (kind bits = 7) */
+#define QR_KEND         0xFFFFFFFFu     /* END element (kind bits = 15) */
 
-#define QR_K_BV         0   /* bounding volume of an array (elm.data & 3 == 1) */
-#define QR_K_PLANE      1   /* srf_t[0] == 1 */
-#define QR_K_QUADRIC    2   /* srf_t[0] == 2 */
-#define QR_K_TWOPLANE   3   /* srf_t[0] == 3 */
-#define QR_K_OPEN       4   /* array with a matrix: opens a transform node */
-#define QR_K_NOP        5   /* array without a matrix / surface without a solver */
-#define QR_K_JUMP       6   /* continue at aux */
-#define QR_K_END        7
-#define QR_K_KIND(w)    ((w) & 7u)
+#define QR_K_BV         0   /* bounding volume of an array (elm.data & 3 == 1); aux = skip distance */
+#define QR_K_PLANE_X    1   /* srf_t[0] == 1, a_map[K] = 0 / 1 / 2; aux = pos[K] (float bits) */
+#define QR_K_PLANE_Y    2
+#define QR_K_PLANE_Z    3
+#define QR_K_QUADRIC    4   /* srf_t[0] == 2 */
+#define QR_K_TWOPLANE   5   /* srf_t[0] == 3 */
+#define QR_K_PLANE_G    6   /* a plane with its own matrix: axis and sign from the descriptor */
+#define QR_K_OPEN       7   /* array with a matrix: transform the ray into the node */
+#define QR_K_CLOSE      8   /* back to the world ray */
+#define QR_K_NOP        9   /* array without a matrix / surface without a solver */
+#define QR_K_JUMP       10  /* continue at aux bytes from here */
+#define QR_K_END        15
+#define QR_K_KIND(w)    ((w) & 15u)
 
-#define QR_KF_CLOSE      8u /* last element of the open transform node */
-#define QR_KF_OWNTRM    16u /* surface with its own matrix, outside any open node */
-#define QR_KF_SKIPCLOSE 32u /* a missed bounding volume skips past the node's last element */
+#define QR_KF_NODE      16u /* world ray in the scratch, local ray in registers (inside a node, or OWN) */
+#define QR_KF_SPARE     32u
+#define QR_KF_SGN       64u /* planes X / Y / Z: a_sgn[K] */
+#define QR_KF_OWN       64u /* quadric / two-plane: its own matrix, outside any node */
 #define QR_K_SURF_OFF(w) ((w) & ~127u)  /* byte offset of the surface record (128 B each) */
 
 #define QR_KC_NEG        1u /* clip lists: rt_ELEM.data < 0 (inner side / accum enter) */
@@ -163,17 +183,21 @@ class qr_kpacker
         ne = h->n_elem;
 
         /* what the list compiler needs of a surface, in one word:
-         * bits 1:0 srf_t[0], 2 array, 3 has a matrix, 4 field shift */
+         * bits 1:0 srf_t[0], 2 array, 3 has a matrix, 4 field shift,
+         * 6:5 a_map[K] (field shift taken off), 7 a_sgn[K] */
         sinfo.resize((size_t)h->n_surf);
         for (int i = 0; i < h->n_surf; i++)
         {
+            const uint32_t mk = (uint32_t)(sf[i].a_map[2] - (sf[i].a_sgn[3] != 0 ? 3 : 0)) & 3u;
             sinfo[i] = (uint8_t)(((uint32_t)sf[i].srf_t[0] & 3u) | (sf[i].srf_t[3] < 0 ? 4u : 0u)
-                               | (sf[i].a_map[3] != 0 ? 8u : 0u) | (sf[i].a_sgn[3] != 0 ? 16u : 0u));
+                               | (sf[i].a_map[3] != 0 ? 8u : 0u) | (sf[i].a_sgn[3] != 0 ? 16u : 0u)
+                               | (mk << 5) | (sf[i].a_sgn[2] != 0 ? 128u : 0u));
         }
 
         out.clear();
-        out.reserve((size_t)ne + (size_t)h->n_tiles + 4u * (size_t)h->n_surf + 64u);
+        out.reserve((size_t)ne + (size_t)ne / 4u + (size_t)h->n_tiles + 4u * (size_t)h->n_surf + 64u);
         nidx.assign((size_t)ne, -1);
+        follow.assign((size_t)ne, -1);
         state.assign((size_t)ne, QR_NIL);
         heads.clear();
         fix.clear();
@@ -198,18 +222,19 @@ class qr_kpacker
         }
         out.push_back(make(QR_KEND, 0));                /* pad: element i + 1 is always loadable */
 
-        /* bounding-volume skip targets: old element -> its sequential index;
-         * the walk arrives there with the node state the skip leaves behind */
+        /* bounding-volume skip slots: the slot right behind the array's last
+         * leaf, in the emission that holds that leaf */
         for (size_t i = 0; i < fix.size(); i++)
         {
-            const int32_t o = fix[i].target;
-            int32_t n = 0;
-            if (o != QR_NIL)
-            {
-                if (o < 0 || o >= ne || nidx[o] < 0 || state[o] != fix[i].state) return -1;
-                n = nidx[o];
-            }
-            out[fix[i].at].aux = n;
+            const int32_t o = fix[i].leaf;
+            if (o < 0 || o >= ne || follow[o] < 0) return -1;
+            /* the volume is met in the node state its last leaf is met in; a
+             * volume inside a node that ends with the node lands on a CLOSE */
+            const int32_t after = state[o] == o ? QR_NIL : state[o];    /* node state behind the leaf */
+            const int32_t want = fix[i].state == o ? QR_NIL : fix[i].state;
+            if (after != want) return -1;
+            if (fix[i].state == o && out[(size_t)follow[o]].w != QR_K_CLOSE) return -1;
+            out[fix[i].at].aux = (follow[o] - fix[i].at) * (int32_t)sizeof(qr_kelem);
         }
 
         /* materials are deduplicated by content: the engine keeps one record
@@ -365,6 +390,8 @@ class qr_kpacker
      * of the open transform node while the list is walked (QR_NIL: none) --
      * the state the reference keeps in ctx_LOCAL(OBJ); state[i] records it
      * per element so that every way of reaching an element agrees on it.
+     * follow[i] is the slot behind element i: where a missed bounding volume
+     * whose array ends with i continues.
      */
     int32_t emit_surf_list(int32_t head)
     {
@@ -385,60 +412,85 @@ class qr_kpacker
             if (nidx[i] >= 0)
             {
                 if (state[i] != lobj) return -1;
-                out.push_back(make(QR_K_JUMP, nidx[i]));
+                const int32_t at = (int32_t)out.size();
+                out.push_back(make(QR_K_JUMP, (nidx[i] - at) * (int32_t)sizeof(qr_kelem)));
                 break;
             }
             const qr_elem &e = el[i];
             if (e.simd < 0 || e.simd >= h->n_surf) return -1;
             const uint32_t si = sinfo[e.simd];
             const bool is_array = (si & 4u) != 0, has_mtx = (si & 8u) != 0;
+            const uint32_t rec = (uint32_t)e.simd << 7;
+            const uint32_t tag = is_array ? 0u : (si & 3u);
             nidx[i] = (int32_t)out.size();
             state[i] = lobj;
 
-            uint32_t f = (is_array || (si & 3u) == 0) ? (uint32_t)QR_K_NOP : (si & 3u);
-            if (!is_array && lobj != QR_NIL)
+            uint32_t f = QR_K_NOP;
+            int32_t  aux = 0;
+            bool     close_after = false;
+            if (e.data_i == 1)
             {
-                if (!(si & 16u)) return -1;             /* child without the field shift */
-                if (i == lobj)
-                {
-                    f |= QR_KF_CLOSE;
-                    lobj = QR_NIL;
-                }
+                /* bounding volume of an array; aux is fixed up at the end */
+                if (has_mtx && is_array) return -1;     /* a bounding volume has no matrix of its own */
+                if (e.data_p < 0 || e.data_p >= ne) return -1;
+                f = QR_K_BV;
+                qr_kfix x;
+                x.at = (int32_t)out.size();
+                x.leaf = e.data_p;                      /* tracer.cpp:4042-4054 */
+                x.state = lobj;
+                fix.push_back(x);
             }
             else
             if (is_array && has_mtx)
             {
-                if (e.data_i == 1) return -1;           /* a bounding volume has no matrix of its own */
+                /* nodes do not nest; should one ever open inside another,
+                 * it starts from the world as the reference's walk does */
+                if (lobj != QR_NIL) out.push_back(make(QR_K_CLOSE, 0));
                 f = QR_K_OPEN;
                 lobj = e.data_p;                        /* tracer.cpp:1492-1496 */
+                if (lobj < 0 || lobj >= ne) return -1;
             }
             else
-            if (is_array && lobj != QR_NIL)
+            if (is_array)
             {
-                return -1;                              /* plain array inside an open node */
+                if (lobj != QR_NIL) return -1;          /* plain array inside an open node */
             }
             else
-            if (!is_array && has_mtx)
             {
-                f |= QR_KF_OWNTRM;
-            }
-            if (e.data_i == 1)
-            {
-                f = (f & ~7u) | QR_K_BV;
-                if (e.data_p < 0 || e.data_p >= ne) return -1;
-
-                qr_kfix x;
-                x.at = nidx[i];
-                x.target = el[e.data_p].next;           /* tracer.cpp:4042-4054 */
-                x.state = lobj;
-                if (e.data_p == lobj)
+                const bool in_node = lobj != QR_NIL;
+                const bool own = !in_node && has_mtx && tag != 0;
+                if (in_node && !(si & 16u)) return -1;  /* child without the field shift */
+                if (tag == 1u)
                 {
-                    f |= QR_KF_SKIPCLOSE;
-                    x.state = QR_NIL;
+                    /* PL_ptr 4062-4136: axis, sign and pos[K] travel with the element */
+                    const uint32_t mk = (si >> 5) & 3u;
+                    if (mk > 2u) return -1;
+                    if (own)
+                    {
+                        f = QR_K_PLANE_G | QR_KF_OWN;
+                    }
+                    else
+                    {
+                        f = (QR_K_PLANE_X + mk) | ((si & 128u) ? QR_KF_SGN : 0u);
+                        memcpy(&aux, &sf[e.simd].pos[mk], 4);
+                    }
                 }
-                fix.push_back(x);
+                else
+                if (tag == 2u) f = QR_K_QUADRIC | (own ? QR_KF_OWN : 0u);
+                else
+                if (tag == 3u) f = QR_K_TWOPLANE | (own ? QR_KF_OWN : 0u);
+                if (in_node || own) f |= QR_KF_NODE;
+                if (own) close_after = true;
+                if (in_node && i == lobj)
+                {
+                    close_after = true;
+                    lobj = QR_NIL;
+                }
             }
-            out.push_back(make(((uint32_t)e.simd << 7) | f, 0));
+            out.push_back(make(rec | f, aux));
+            /* a skip from inside the node lands ON the CLOSE */
+            follow[i] = (int32_t)out.size();
+            if (close_after) out.push_back(make(QR_K_CLOSE, 0));
             i = e.next;
         }
         return first;
@@ -512,9 +564,9 @@ class qr_kpacker
     const int32_t        *tl;
     int                   ne;
     qr_blob_header        k;
-    struct qr_kfix { int32_t at, target, state; };      /* BV element, old skip target, state there */
+    struct qr_kfix { int32_t at, leaf, state; };        /* BV slot, the array's last leaf, node state at the BV */
     std::vector<uint8_t>  sinfo;
-    std::vector<int32_t>  state, nidx, k_tiles, k_srf, k_lgt, k_clip, shadow;
+    std::vector<int32_t>  state, nidx, follow, k_tiles, k_srf, k_lgt, k_clip, shadow;
     std::vector<int32_t>  mat_map, mat_uniq;            /* blob material -> table index, table index -> blob material */
     std::unordered_map<uint64_t, std::vector<int32_t> > mat_bucket;
     std::vector<qr_kelem> out;

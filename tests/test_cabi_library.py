@@ -66,19 +66,19 @@ def test_product_does_not_reference_the_oracle():
 
 
 def test_big_frame_kernel_register_allocation():
-    """The 1024-thread x 64-register build of the kernel is what big frames
-    run, and ptxas has two allocation regimes for it: ~200 bytes of spill
-    stores (1.87 ms per 1080p 4xAA frame) or ~480 (2.6 ms) -- harmless-looking
-    edits of the list walk flip it.  The build log says which
-    one a change landed in, before any GPU sees it."""
+    """The 768-thread x 80-register build of the kernel is what big frames run.
+    ptxas's allocation for it is sensitive to harmless-looking edits of the
+    list walk: the build log says where a change landed before
+    any GPU sees it.  Round 2: ~120 bytes of spill stores, none inside the walk
+    loop (the 1024 x 64 build spills p_obj into the loop and is not used)."""
     log = os.path.join(ROOT, "quadray-engine_b200", "lib", "ptxas.log")
     if not os.path.exists(log):
         pytest.skip("no ptxas log (library not built here)")
     text = open(log).read()
-    m = re.search(r"Compiling entry function '_Z16qr_render_kernelILb1ELi1024ELi1EEv9qr_launch'.*?\n"
+    m = re.search(r"Compiling entry function '_Z16qr_render_kernelILb1ELi768ELi1EEv9qr_launch'.*?\n"
                   r".*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n"
                   r".*?Used (\d+) registers", text, flags=re.S)
-    assert m, "1024-thread staged kernel not found in ptxas.log"
+    assert m, "768-thread staged kernel not found in ptxas.log"
     stack, st, ld, regs = (int(x) for x in m.groups())
-    assert regs == 64
-    assert st <= 300 and ld <= 300, (stack, st, ld)
+    assert regs == 80
+    assert st <= 160 and ld <= 120, (stack, st, ld)
