@@ -234,7 +234,10 @@ class qr_kpacker
             const int32_t want = fix[i].state == o ? QR_NIL : fix[i].state;
             if (after != want) return -1;
             if (fix[i].state == o && out[(size_t)follow[o]].w != QR_K_CLOSE) return -1;
-            out[fix[i].at].aux = (follow[o] - fix[i].at) * (int32_t)sizeof(qr_kelem);
+            /* a volume outside the node need not stop at the node's CLOSE */
+            int32_t to = follow[o];
+            if (fix[i].state == QR_NIL && out[(size_t)to].w == QR_K_CLOSE) to++;
+            out[fix[i].at].aux = (to - fix[i].at) * (int32_t)sizeof(qr_kelem);
         }
 
         /* materials are deduplicated by content: the engine keeps one record
