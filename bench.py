@@ -25,9 +25,15 @@ A step = one render0 pass over one frame (8 294 400 primary samples).
 N > 1 (torchrun, one rank per GPU): strong scaling of one frame.  Tile rows are
 dealt round-robin (rank r renders rows r, r + N, ...); every rank stores its
 pixels straight into rank 0's framebuffer over NVLink (the buffer is shared
-through a CUDA IPC handle, qr_frame_ipc_*), a tiny NCCL all-reduce tells rank 0
-that everybody is done.  --gather nccl renders into a local buffer and gathers
-the rows with one NCCL gather instead.
+through a CUDA IPC handle, qr_frame_ipc_*); the last warp of every rank's
+kernel bumps a counter behind that framebuffer (over NVLink as well) and rank
+0's stream waits for it (qr_render_rows_notify / qr_wait_notify): no
+collective on the data path.  --gather nccl renders into a local buffer and
+gathers the rows with one NCCL gather instead.
+e2e at N > 1: every rank uploads the scene from host memory and renders its
+rows straight into ONE page-locked host frame shared by all ranks (POSIX
+shared memory), two frames in flight; the pixels leave every GPU over its own
+PCIe link.
 """
 import argparse
 import json
@@ -47,6 +53,24 @@ METRIC = "Mrays/s at 1080p 4xAA (frame ms = ms_per_step)"
 UNIT = "Mrays/s"
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "qr_ref_harness")
 REF_ARGS = ["-s", "demo03", "-x", "1920", "-y", "1080", "-a", "2", "-g", "-u"]
+REF_ARGS_UPDATE = ["-s", "demo03", "-x", "1920", "-y", "1080", "-a", "2", "-g"]
+
+
+def make_config(meta, world, gather):
+    """The workload description: IDENTICAL in both arms (the driver compares
+    it), so it holds no measured value."""
+    return {
+        "workload": WORKLOAD_DESC, "x_res": meta["x_res"], "y_res": meta["y_res"], "fsaa": "4x", "gamma": True,
+        "rays_per_frame": meta["rays"]["total"],
+        "primary_samples_per_frame": meta["rays"]["primary"],
+        "n_gpus": world,
+        "l2": "GPU arm: flushed between timed iterations (256 MB fill); reference arm: host caches as they are",
+        "sharding": "single GPU" if world == 1 else
+                    "GPU arm: tile rows dealt round-robin over %d ranks (%s); reference arm: rank 0's host cores"
+                    % (world, "P2P stores into rank 0's framebuffer over NVLink" if gather == "p2p" else "NCCL gather"),
+        "timing": "GPU arm: CUDA events per step on the launching stream, summed, max over ranks; "
+                  "reference arm: wall clock per frame inside the harness, median",
+    }
 
 
 # ---------------------------------------------------------------- helpers ---
@@ -106,6 +130,15 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def kernel_source_hash():
+    """sha256 over the sources the render kernel is compiled from."""
+    import hashlib
+    hsh = hashlib.sha256()
+    for f in ("csrc/qr_b200.cu", "csrc/qr_core.cuh", "csrc/qr_kscene.h"):
+        hsh.update(open(os.path.join(ROOT, "quadray-engine_b200", f), "rb").read())
+    return hsh.hexdigest()
+
+
 def load_workload():
     import __graft_entry__ as ge
     blob, ref_frame, meta = ge.load_golden(WORKLOAD)
@@ -119,11 +152,11 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(frames, warmup, threads):
+def run_reference(frames, warmup, threads, ref_args=None, extra=()):
     """The unmodified reference on the host cores; returns dict or None."""
     if not os.path.exists(REF_HARNESS):
         return None
-    cmd = [REF_HARNESS] + REF_ARGS + ["-t", str(threads), "-f", str(frames), "-w", str(warmup)]
+    cmd = [REF_HARNESS] + list(ref_args or REF_ARGS) + ["-t", str(threads), "-f", str(frames), "-w", str(warmup)] + list(extra)
     try:
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900, check=True)
         return json.loads(out.stdout.decode().strip().splitlines()[-1])
@@ -142,19 +175,33 @@ def run_port(blob, meta, rows):
     return dt / frac
 
 
-def cpu_baseline(blob, meta, frames, warmup):
+def cpu_baseline(blob, meta, frames, warmup, variants=False):
     """cpu_baseline object: the reference timed on this box's host cores."""
     rays = meta["rays"]["total"]
     threads = min(host_threads(), 120)
     ref = run_reference(frames, warmup, threads)
     if ref is not None:
         ms = ref["ms_med"]
-        return {"value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "cores": ref["threads"],
-                "kind": "reference", "frame_ms": ms, "frame_ms_min": ref["ms_min"],
-                "simd": ref["simd"],
-                "sample": "%d frames (+%d warm-up) of the same 1080p 4xAA demo03 frame, render-only "
-                          "(lists frozen with RT_OPTS_UPDATE_EXT0), %d pinned threads, target %s"
-                          % (frames, warmup, ref["threads"], ref["simd"])}, ms
+        out = {"value": rays / (ms * 1e-3) / 1e6, "unit": UNIT, "cores": ref["threads"],
+               "kind": "reference", "frame_ms": ms, "frame_ms_min": ref["ms_min"],
+               "simd": ref["simd"],
+               "sample": "%d frames (+%d warm-up) of the same 1080p 4xAA demo03 frame, render-only "
+                         "(lists frozen with RT_OPTS_UPDATE_EXT0), %d pinned threads, target %s"
+                         % (frames, warmup, ref["threads"], ref["simd"])}
+        if variants:
+            # BASELINE.md section 3: the plain AVX-512 target, one thread, and
+            # update + render (what rt_Scene::render costs a caller) beside it
+            var = {}
+            for name, ra, th, extra, nfr in (
+                    ("avx512_512x1v2_all_threads_render_only", REF_ARGS, threads, ["-n", "512", "-k", "1", "-v", "2"], 20),
+                    ("best_target_1_thread_render_only", REF_ARGS, 1, [], 5),
+                    ("best_target_all_threads_update_and_render", REF_ARGS_UPDATE, threads, [], 20)):
+                r = run_reference(nfr, 2, th, ra, extra)
+                if r is not None:
+                    var[name] = {"frame_ms": r["ms_med"], "threads": r["threads"], "simd": r["simd"],
+                                 "value": rays / (r["ms_med"] * 1e-3) / 1e6, "frames": nfr}
+            out["variants"] = var
+        return out, ms
     rows = 64
     sec = run_port(blob, meta, rows)
     return {"value": rays / sec / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
@@ -188,8 +235,7 @@ def main_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC, "rays_per_frame": rays,
-                   "primary_samples_per_frame": meta["rays"]["primary"]},
+        "config": make_config(meta, max(args.gpus, 1), args.gather),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -272,6 +318,15 @@ def main_gpu(args, rank, world, local_rank):
                 sys.stderr.write("bench.py: falling back to the NCCL gather\n")
         elif rank == 0:
             frame_d = torch.as_tensor(_DevArray(frame_ptr, (h, x_row)), device=dev)
+    notify_ptr = None
+    frames_done = [0]
+    if gather == "p2p":
+        # completion counter 0 behind rank 0's framebuffer, as every rank maps it
+        notify_ptr = ctx.frame_notify_slot(frame_ptr, 0)
+        if rank == 0:
+            torch.as_tensor(_DevArray(notify_ptr, (1,)), device=dev).zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
     if gather == "nccl":
         # frame padded to whole slots; tile row t = k * world + r sits at view[k, r]
         full_d = torch.zeros((slots * world * tile_h, x_row), dtype=torch.int32, device=dev)
@@ -286,22 +341,33 @@ def main_gpu(args, rank, world, local_rank):
 
     def finish_frame():
         """After this rank's kernel: make the frame complete on rank 0 (the one
-        exchange step per frame)."""
-        if gather == "p2p":
-            dist.all_reduce(token)                  # everybody's stores have landed
-        elif gather == "nccl":
+        exchange step per frame; --gather nccl only, the P2P path signals from
+        the kernel)."""
+        if gather == "nccl":
             mine_d.copy_(view[:, rank])
             dist.gather(mine_d, gather_list=gather_d, dst=0)
             if rank == 0:
                 for r in range(1, world):
                     view[:, r].copy_(gather_d[r])
 
+    def render_shard():
+        """This rank's tile rows of one frame; with the P2P gather the kernel
+        bumps the counter behind rank 0's frame and rank 0's stream waits until
+        all ranks have (frames so far * ranks)."""
+        if gather == "p2p":
+            frames_done[0] += 1
+            ctx.render_rows_notify(frame_ptr, x_row, rank, world, notify_ptr)
+            if rank == 0:
+                ctx.wait_notify(notify_ptr, frames_done[0] * world)
+        else:
+            ctx.render_rows(frame_ptr, x_row, rank, world)
+
     def step_device(ev0, ev1):
         flush.fill_(rank + 1)                       # evict L2 between timed iterations
         qstream.wait_stream(cur)
         ev0.record(qstream)
-        ctx.render_rows(frame_ptr, x_row, rank, world)
-        if world > 1:
+        render_shard()
+        if gather == "nccl":
             cur.wait_stream(qstream)
             finish_frame()
             ev1.record(cur)
@@ -366,17 +432,28 @@ def main_gpu(args, rank, world, local_rank):
         kern_ms = statistics.mean(ks)
         peak = ctx.fp32_peak()
         ops = meta["ieee_ops"]["total"]
-        traffic = None
+        # DRAM traffic of the kernel comes from the committed ncu capture -- only
+        # if that capture is of THIS kernel: same sources (hash), same launch shape
+        traffic, traffic_note = None, "no profiles/ncu_summary.json"
         ncu_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(ncu_json):
             try:
-                traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+                nj = json.load(open(ncu_json))
+                kinfo = ctx.kernel_info()
+                if nj.get("kernel_source_sha256") != kernel_source_hash():
+                    traffic_note = "ncu_summary.json was captured from other kernel sources (%s...)" \
+                                   % str(nj.get("kernel_source_sha256"))[:12]
+                elif nj.get("threads_per_cta") != kinfo["threads_per_cta"]:
+                    traffic_note = "ncu_summary.json was captured at another launch shape"
+                else:
+                    traffic = nj.get("dram_bytes_per_launch")
+                    traffic_note = "ncu --set full, commit %s, %s" % (nj.get("commit"), nj.get("kernel"))
+            except Exception as exc:
+                traffic_note = "ncu_summary.json unreadable: %r" % (exc,)
         achieved = ops / (kern_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak if peak else None, "traffic": traffic,
+            "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_note,
             "kernel": "qr_render_kernel", "kernel_ms": kern_ms,
             "algorithmic_ops_per_launch": ops,
             "peak_source": "measured on this GPU by qr_fp32_peak (separately rounded FMUL+FADD, no FMA; "
@@ -402,33 +479,102 @@ def main_gpu(args, rank, world, local_rank):
     h2d = int(blob_h.size)
     d2h = int(h * w * 4) if rank == 0 else 0
 
-    def step_e2e():
-        if world == 1:
+    e2e_path_n = None
+    if world == 1:
+        def step_e2e():
             ctx.upload(blob_h)
             ctx.render(hf, x_row)
-        else:
-            ctx.upload(blob_h)
-            qstream.wait_stream(cur)
-            ctx.render_rows(frame_ptr, x_row, rank, world)
-            cur.wait_stream(qstream)
-            finish_frame()
-            if rank == 0:
-                host_frame.copy_(frame_d, non_blocking=True)
-            torch.cuda.synchronize(dev)
 
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        for _ in range(3):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_parity = int((hf[:, :w] != ref_frame).sum())
+    else:
+        # ONE page-locked host frame (two of them: two frames in flight) shared by
+        # all ranks through POSIX shared memory; every rank renders its tile rows
+        # straight into it, so the pixels leave each GPU over its own PCIe link
+        # while its kernel runs.  Per step and rank: qr_scene_upload (pack +
+        # pinned H2D, into the scene slot the GPU is not reading) +
+        # qr_render_rows(shared host frame) + wait for the PREVIOUS frame's
+        # kernel + a flag in the shared segment; rank 0 sees the previous frame
+        # complete when every rank's flag has reached it, and reads it.
+        import mmap
+        fbytes = h * x_row * 4
+        seg_bytes = 2 * fbytes + 4096
+        shm_name = "/dev/shm/qr_b200_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"))
+        if rank == 0:
+            fd = os.open(shm_name, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, seg_bytes)
+        dist.barrier()
+        if rank != 0:
+            fd = os.open(shm_name, os.O_RDWR)
+        seg = mmap.mmap(fd, seg_bytes)
+        seg_np = np.frombuffer(seg, dtype=np.uint8)
+        seg_dev = ctx.host_register(seg_np.ctypes.data, seg_bytes)
+        frames_h = [seg_np[k * fbytes:(k + 1) * fbytes].view(np.uint32).reshape(h, x_row) for k in range(2)]
+        flags = seg_np[2 * fbytes:2 * fbytes + 8 * (world + 1)].view(np.int64)   # [rank]: rows done, [world]: consumed
+        if rank == 0:
+            flags[:] = 0
+        dist.barrier()
+        ctx.pipeline(True)
+        evq = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = [0]
+
+        def run_sharded(n):
+            """n frames; returns after the last one is complete in host memory."""
+            base = seen[0]
+            for i in range(n + 1):
+                k = base + i
+                if i < n:
+                    ctx.upload(blob_h)
+                    while int(flags[world]) < k - 1:        # the host frame k uses is free (frame k - 2 consumed)
+                        pass
+                    ctx.render_rows(seg_dev + (k & 1) * fbytes, x_row, rank, world)
+                    evq[k & 1].record(qstream)
+                if i > 0:
+                    evq[(k - 1) & 1].synchronize()          # this rank's rows of frame k - 1 are in host memory
+                    flags[rank] = k                         # ... says so to rank 0
+                    if rank == 0:
+                        while int(flags[:world].min()) < k:
+                            pass
+                        _ = int(frames_h[(k - 1) & 1][h // 2, w // 2])      # the step's result is read on the host
+                        flags[world] = k                    # ... and its buffer handed back
+            seen[0] = base + n
+
+        run_sharded(3)
+        barrier()
+        t0 = time.perf_counter()
+        run_sharded(args.steps)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        e2e_parity = int((frames_h[(seen[0] - 1) & 1][:, :w] != ref_frame).sum()) if rank == 0 else None
+        ctx.pipeline(False)
+        ctx.upload(blob_h)
+        ctx.sync()
+        ctx.host_unregister(seg_np.ctypes.data)
+        d2h = int(sum(min(tile_h, h - t * tile_h) for t in range(rank, tls_col, world)) * w * 4)
+        e2e_path_n = ("per step and rank: qr_scene_upload(host blob: pack + pinned H2D, two scene slots) + "
+                      "qr_render_rows(its tile rows, stored by the kernel straight into ONE page-locked host frame "
+                      "shared by all ranks, over each GPU's own PCIe link) + wait for the previous frame; "
+                      "two frames in flight; rank 0 reads the frame when every rank has flagged it")
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_name)
+            except OSError:
+                pass
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    bytes_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bytes_t, op=dist.ReduceOp.SUM)
     e2e_s = float(t.item())
-    e2e_parity = int((hf[:, :w] != ref_frame).sum()) if rank == 0 else None
+    h2d, d2h = int(bytes_t[0].item()), int(bytes_t[1].item())
 
     # the same through the pipelined calls (N = 1): scene N + 1 is packed and
     # copied while frame N renders; every step still uploads its scene from
@@ -458,36 +604,74 @@ def main_gpu(args, rank, world, local_rank):
         ctx.pipeline(False)
         ctx.upload(blob_h)
 
+    # ---- the single-process multi-GPU context (what the drop-in render0 uses
+    # with QR_B200_DEVICES=0,1,..): rank 0 opens one over all GPUs of the job
+    # while the other ranks idle, renders the 1080p workload and the 4K frame
+    # of BASELINE.json config 4, and reports parity and frame time
+    single = None
+    if world > 1:
+        barrier()
+        # the other ranks wait on the HOST (gloo): an NCCL barrier would keep a
+        # spinning kernel on their GPUs, which rank 0's context is rendering on
+        idle = dist.new_group(backend="gloo")
+        if rank == 0:
+            try:
+                c2 = pkg.Context(list(range(world)))
+                single = {"devices": world}
+                for tag, fx in (("1080p", None), ("4k", "demo03_4k_a4gh")):
+                    if fx is None:
+                        b2, want, crc = blob, ref_frame, None
+                    else:
+                        b2, crc, _m = ge.load_golden_hashed(fx)
+                        want = None
+                    c2.upload(b2)
+                    got2 = c2.render_frame()
+                    ts = []
+                    for _ in range(8):
+                        c2.sync()
+                        t1 = time.perf_counter()
+                        c2.render(None)
+                        c2.sync()
+                        ts.append((time.perf_counter() - t1) * 1e3)
+                    if want is not None:
+                        differ = int((got2 != want).sum())
+                    else:
+                        differ = int((ge.row_crcs(got2) != crc).sum())
+                    single[tag] = {"frame_ms": statistics.median(ts),
+                                   ("pixels_differ" if want is not None else "rows_differ"): differ}
+                c2.close()
+            except Exception as exc:
+                single = {"error": repr(exc)}
+        dist.barrier(group=idle)
+        barrier()
+
     info = ctx.kernel_info()
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        base, _ = cpu_baseline(blob, meta, 100, 3)
+        base, _ = cpu_baseline(blob, meta, 100, 3, variants=True)
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         sharding = {"none": "single GPU",
                     "p2p": "tile rows dealt round-robin; every rank stores into rank 0's framebuffer over NVLink "
-                           "(CUDA IPC), one tiny NCCL all-reduce per frame as completion signal",
+                           "(CUDA IPC); the last warp of each rank's kernel bumps a counter behind that frame, rank 0's "
+                           "stream waits for it (no collective)",
                     "nccl": "tile rows dealt round-robin; one NCCL gather to rank 0 per frame"}[gather]
         line = {
             "metric": METRIC, "value": rays * args.steps / (dev_ms * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "fps": 1e3 / ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC, "x_res": w, "y_res": h, "fsaa": "4x", "gamma": True,
-                       "rays_per_frame": rays, "rays_per_frame_measured": rays_measured,
-                       "primary_samples_per_frame": meta["rays"]["primary"],
-                       "primary_Msamples_per_s": meta["rays"]["primary"] * args.steps / (dev_ms * 1e-3) / 1e6,
-                       "l2": "flushed between timed iterations (256 MB fill)",
-                       "sharding": sharding,
-                       "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+            "dtype": "f32", "data": "synthetic", "impl": "ours",
+            "config": make_config(meta, world, gather),
+            "rays_per_frame_measured": rays_measured,
+            "primary_Msamples_per_s": meta["rays"]["primary"] * args.steps / (dev_ms * 1e-3) / 1e6,
+            "sharding": sharding,
             "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": UNIT,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "qr_scene_upload(host blob: pack + pinned H2D) + qr_render(page-locked host frame, written by the kernel over PCIe)"
-                            if world == 1 else
-                            "qr_scene_upload + qr_render_rows + frame exchange (%s) + D2H on rank 0" % gather,
+                            if world == 1 else e2e_path_n,
                     "pixels_differ_vs_reference_cpu_frame": e2e_parity},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -510,6 +694,8 @@ def main_gpu(args, rank, world, local_rank):
                 "synchronous": {"value": sync["value"], "ms_per_step": sync["ms_per_step"], "path": sync["path"],
                                 "pixels_differ_vs_reference_cpu_frame": sync["pixels_differ_vs_reference_cpu_frame"]},
             }
+        if single is not None:
+            line["single_process_ctx"] = single
         if roofline is not None:
             line["roofline"] = roofline
         if base is not None:

@@ -79,6 +79,11 @@ int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes);
  *                   any other frame goes through pinned staging in two chunks
  *                   whose copy overlaps the rendering of the next.
  *   frame  == NULL: render only (asynchronous; see qr_sync / qr_frame_device).
+ * Alignment: frame buffers (host or device, here and in qr_render_device /
+ * qr_render_rows / qr_render_fetch) need 4-byte alignment only.  The kernel
+ * issues 128-bit stores where the ADDRESS of a group of four pixels is
+ * 16-byte aligned and 32-bit stores elsewhere, so a frame at base + 4 or an
+ * odd stride renders correctly (a little slower).
  */
 int qr_render(qr_ctx *ctx, uint32_t *frame, int stride);
 
@@ -102,6 +107,38 @@ int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y
  * stores them and no gather pass is needed.
  */
 int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, int tile_row_step);
+
+/*
+ * Completion signal of sharded frames without a collective.  The framebuffer
+ * of the library (qr_frame_device, and what qr_frame_ipc_open maps on the other
+ * ranks) is followed by 16 counters; qr_frame_notify_slot returns the device
+ * address of one of them for a given mapping of that buffer.
+ *   qr_render_rows_notify  as qr_render_rows; in addition the kernel adds 1
+ *                          (system scope) to *notify_dev when every pixel of
+ *                          this launch is visible to the owner of the frame --
+ *                          from a peer GPU the counter is reached over NVLink,
+ *                          like the pixels
+ *   qr_wait_notify         the context's stream waits until the counter has
+ *                          reached "target" (counters only ever grow; the
+ *                          comparison is wrap-around safe), e.g. target =
+ *                          frames so far * ranks on the rank that owns the frame
+ * This replaces the reference's worker join (rt_FUNC_RENDER returning on all
+ * threads, core/engine/engine.h:71-74) across GPUs.
+ */
+int qr_frame_notify_slot(qr_ctx *ctx, uint32_t *frame_dev, int index, uint32_t **slot_dev);
+
+/*
+ * A HOST framebuffer shared by several processes (one rank per GPU, e.g. a
+ * POSIX shared-memory segment, the role RooT's XShm image plays): every rank
+ * page-locks its mapping and renders its tile rows straight into it with
+ * qr_render_rows(dev_ptr, ...) -- the pixels leave every GPU over its own PCIe
+ * link while the kernel runs, no gather to one GPU and no D2H pass.
+ */
+int qr_host_register(qr_ctx *ctx, void *host, size_t bytes, uint32_t **dev_ptr);
+int qr_host_unregister(qr_ctx *ctx, void *host);
+int qr_render_rows_notify(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0, int tile_row_step,
+                          uint32_t *notify_dev);
+int qr_wait_notify(qr_ctx *ctx, uint32_t *notify_dev, uint32_t target);
 
 /*
  * Pipelined frames: the engine's update phases of frame N + 1 (rt_Scene::render

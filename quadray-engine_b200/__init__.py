@@ -28,6 +28,7 @@ SYMBOLS = (
     "qr_frame_ipc_export", "qr_frame_ipc_open", "qr_frame_ipc_close", "qr_dump_hits",
     "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
     "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_fetch", "qr_render_end",
+    "qr_frame_notify_slot", "qr_render_rows_notify", "qr_wait_notify", "qr_host_register", "qr_host_unregister",
 )
 
 
@@ -71,6 +72,16 @@ def load_library():
     lib.qr_render_device.restype = ci
     lib.qr_render_rows.argtypes = [vp, vp, ci, ci, ci]
     lib.qr_render_rows.restype = ci
+    lib.qr_host_register.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
+    lib.qr_host_register.restype = ci
+    lib.qr_host_unregister.argtypes = [vp, vp]
+    lib.qr_host_unregister.restype = ci
+    lib.qr_frame_notify_slot.argtypes = [vp, vp, ci, ctypes.POINTER(vp)]
+    lib.qr_frame_notify_slot.restype = ci
+    lib.qr_render_rows_notify.argtypes = [vp, vp, ci, ci, ci, vp]
+    lib.qr_render_rows_notify.restype = ci
+    lib.qr_wait_notify.argtypes = [vp, vp, ctypes.c_uint32]
+    lib.qr_wait_notify.restype = ci
     lib.qr_frame_ipc_export.argtypes = [vp, vp]
     lib.qr_frame_ipc_export.restype = ci
     lib.qr_frame_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
@@ -214,6 +225,34 @@ class Context(object):
         full-frame geometry (possibly another GPU's, see frame_ipc_open)."""
         self._check(self.lib.qr_render_rows(self.h, ctypes.c_void_p(dev_ptr), int(stride),
                                             int(tile_row0), int(tile_row_step)))
+
+    def host_register(self, host_ptr, nbytes):
+        """Page-lock a host buffer (e.g. a shared-memory frame) for this context's
+        GPU; returns the device pointer the kernels store through."""
+        out = ctypes.c_void_p()
+        self._check(self.lib.qr_host_register(self.h, ctypes.c_void_p(host_ptr), int(nbytes), ctypes.byref(out)))
+        return out.value
+
+    def host_unregister(self, host_ptr):
+        self._check(self.lib.qr_host_unregister(self.h, ctypes.c_void_p(host_ptr)))
+
+    def frame_notify_slot(self, frame_dev_ptr, index):
+        """Device address of completion counter "index" behind the library's
+        framebuffer as mapped at frame_dev_ptr (own or opened through IPC)."""
+        out = ctypes.c_void_p()
+        self._check(self.lib.qr_frame_notify_slot(self.h, ctypes.c_void_p(frame_dev_ptr), int(index),
+                                                  ctypes.byref(out)))
+        return out.value
+
+    def render_rows_notify(self, dev_ptr, stride, tile_row0, tile_row_step, notify_ptr):
+        """render_rows + the kernel adds 1 to *notify_ptr when its pixels are visible."""
+        self._check(self.lib.qr_render_rows_notify(self.h, ctypes.c_void_p(dev_ptr), int(stride),
+                                                   int(tile_row0), int(tile_row_step),
+                                                   ctypes.c_void_p(notify_ptr)))
+
+    def wait_notify(self, notify_ptr, target):
+        """The context's stream waits until the counter has reached target."""
+        self._check(self.lib.qr_wait_notify(self.h, ctypes.c_void_p(notify_ptr), ctypes.c_uint32(target & 0xFFFFFFFF)))
 
     def frame_ipc_export(self):
         """64-byte CUDA IPC handle of GPU 0's framebuffer (bytes)."""

@@ -101,9 +101,14 @@ struct qr_launch
     int                 ty_step;    /* distance between its tile rows (1 = contiguous band) */
     int                 n_trows;    /* number of tile rows: ty0, ty0 + ty_step, ... */
     uint32_t            stage_bytes;/* blob prefix staged in smem, 0 = none */
-    unsigned int       *queue;      /* work-item counter */
+    unsigned int       *queue;      /* work-item counter: never reset, this launch's items start at ... */
+    unsigned int        queue_base; /* ... this value (every warp draws exactly one item too many, so
+                                       the host knows where the counter stands after the launch) */
     unsigned long long *rays;       /* [4] ray counters */
     float              *t_out;      /* dump mode, or NULL */
+    unsigned int       *notify;     /* or NULL: +1 (system scope) when all pixels of this launch are visible */
+    unsigned int       *done;       /* warps of this launch that have finished (notify != NULL) */
+    unsigned int        n_warps;    /* warps of this launch */
 };
 
 extern __shared__ __align__(128) uint8_t qr_smem[];
@@ -201,7 +206,7 @@ qr_render_kernel(const qr_launch p)
     /* one work item = one packet (a 4 x bh pixel block of a tile); the queue
      * is read one item ahead, so the atomic's latency hides behind a trace */
     unsigned int item = 0;
-    if (lane == 0) item = atomicAdd(p.queue, 1u);
+    if (lane == 0) item = atomicAdd(p.queue, 1u) - p.queue_base;
     item = __shfl_sync(0xFFFFFFFFu, item, 0);
 
     while (item < n_items)
@@ -272,7 +277,9 @@ qr_render_kernel(const qr_launch p)
             {
                 const int xq = x0;
                 uint32_t *dst = p.frame + (size_t)(y0 + lane) * p.stride + xq;
-                if (xq + 3 < x_res && ((((size_t)(y0 + lane) * p.stride + xq) & 3) == 0))
+                /* one 128-bit store when the ADDRESS allows it (a caller's frame
+                 * or stride need not be 16-byte aligned) */
+                if (xq + 3 < x_res && (((size_t)dst & 15) == 0))
                 {
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
                 }
@@ -289,7 +296,7 @@ qr_render_kernel(const qr_launch p)
          * waits behind the one in progress while other warps run dry, which
          * doubles the tail of a launch; the atomic's latency is hidden by the
          * other warps of the SM */
-        if (lane == 0) item = atomicAdd(p.queue, 1u);
+        if (lane == 0) item = atomicAdd(p.queue, 1u) - p.queue_base;
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
     }
 
@@ -308,6 +315,42 @@ qr_render_kernel(const qr_launch p)
         atomicAdd(&p.rays[2], (unsigned long long)c2);
         atomicAdd(&p.rays[3], (unsigned long long)c3);
     }
+
+    /* completion signal: the last warp of the launch to get here tells the
+     * owner of the frame (possibly another GPU: the word sits behind rank 0's
+     * framebuffer, reached over NVLink like the pixels) that every pixel of
+     * this launch is visible */
+    if (p.notify != NULL)
+    {
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0)
+        {
+            if (atomicAdd(p.done, 1u) == p.n_warps - 1u)
+            {
+                *p.done = 0u;
+                __threadfence();
+                atomicAdd_system(p.notify, 1u);
+            }
+        }
+    }
+}
+
+/* a rank without rows of its own still owes its completion signal */
+__global__ void qr_add_kernel(unsigned int *flag)
+{
+    atomicAdd_system(flag, 1u);
+}
+
+/* rank 0's stream waits here until *flag has reached "target" (wrap-around safe) */
+__global__ void qr_wait_kernel(unsigned int *flag, unsigned int target)
+{
+    volatile unsigned int *f = flag;
+    while ((int)(*f - target) < 0)
+    {
+        __nanosleep(64);
+    }
+    __threadfence_system();
 }
 
 /*
@@ -351,6 +394,7 @@ static qr_kernel_fn qr_kernel_of(bool staged, int shape)
 }
 
 #define QR_MAX_DEV 16
+#define QR_NOTIFY_SLOTS 16  /* completion counters behind the library's framebuffer */
 #define QR_COPY_THREADS 16  /* upper bound; QR_B200_COPY_THREADS (default 4): one thread moves ~11 GB/s,
                                a 1080p frame in 0.75 ms, four in 0.25 */
 #define QR_MAX_CHUNKS 8     /* qr_render to a host frame: render / D2H pipeline depth */
@@ -374,7 +418,8 @@ struct qr_dev
     uint32_t       *frame_d;    size_t frame_cap;   /* bytes */
     uint32_t       *frame_h;    size_t frame_hcap;  /* pinned (dev 0 only) */
     float          *t_d;        size_t t_cap;
-    unsigned int   *queue_d;
+    unsigned int   *queue_d;                        /* [0] work-item counter, [1] finished warps */
+    unsigned int    queue_base;                     /* where the counter stands (see qr_launch) */
     unsigned long long *rays_d;
     int             sm_count;
     int             ctas_per_sm;
@@ -406,7 +451,10 @@ struct qr_ctx
     int             chunks;         /* qr_render(host frame) pipeline depth on one GPU, 0 = automatic */
     int             pin_frames;     /* QR_B200_PIN_FRAME=1: page-lock the caller's framebuffer on first use */
     int             zerocopy;       /* store pixels straight into a page-locked host frame (QR_B200_ZEROCOPY=0: off) */
-    void           *pinned[4];      /* framebuffers registered that way */
+    void           *pinned[4];      /* framebuffers registered that way ... */
+    size_t          pinned_bytes[4];/* ... and how much of them */
+    unsigned        pinned_age[4];  /* last use (the oldest entry is evicted) */
+    unsigned        pin_clock;
     int             pipelined;      /* qr_pipeline(ctx, 1): scenes alternate between two slots */
     int             slot;           /* slot of the current scene */
     bool            pending[2];     /* a frame begun in this slot has not been collected */
@@ -431,6 +479,10 @@ struct qr_ctx
 };
 
 static thread_local char g_init_err[512] = "";
+
+/* CPU affinity of the process at load time (helper threads inherit it) */
+static cpu_set_t g_load_affinity;
+static const bool g_load_affinity_ok = sched_getaffinity(0, sizeof(g_load_affinity), &g_load_affinity) == 0;
 
 static int qr_fail(qr_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -509,7 +561,8 @@ extern "C" int qr_init(const int *devices, int ndev, qr_ctx **out)
         ||  (e = cudaEventCreate(&d.ev0)) != cudaSuccess
         ||  (e = cudaEventCreate(&d.ev1)) != cudaSuccess
         ||  (e = cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming)) != cudaSuccess
-        ||  (e = cudaMalloc(&d.queue_d, sizeof(unsigned int))) != cudaSuccess
+        ||  (e = cudaMalloc(&d.queue_d, 2 * sizeof(unsigned int))) != cudaSuccess
+        ||  (e = cudaMemset(d.queue_d, 0, 2 * sizeof(unsigned int))) != cudaSuccess
         ||  (e = cudaMalloc(&d.rays_d, 4 * sizeof(unsigned long long))) != cudaSuccess
         ||  (e = cudaMemset(d.rays_d, 0, 4 * sizeof(unsigned long long))) != cudaSuccess)
         {
@@ -749,6 +802,10 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     }
     const size_t n = pk.bytes();
 
+    /* from here on the slot, the header and the launch shape change step by
+     * step: the context has no scene until every step has succeeded */
+    ctx->have_scene = false;
+
     qr_dev &d0 = ctx->dev[0];
     QR_CUDA(ctx, cudaSetDevice(d0.id));
     if (ctx->pipelined)
@@ -803,7 +860,6 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     }
 
     ctx->hdr = *h;
-    ctx->have_scene = true;
 
     /*
      * Launch shape by the amount of work of a full-frame launch.  The walk is
@@ -859,12 +915,14 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         }
         d.ctas_per_sm = nb;
     }
+    ctx->have_scene = true;
     return QR_OK;
 }
 
 /* tile rows ty0, ty0 + step, ... (n of them) on GPU i into frame_dev */
 static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
-                          int ty0, int step, int n, float *t_out, bool first = true)
+                          int ty0, int step, int n, float *t_out, bool first = true,
+                          unsigned int *notify = NULL)
 {
     qr_dev &d = ctx->dev[i];
     QR_CUDA(ctx, cudaSetDevice(d.id));
@@ -885,6 +943,8 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     p.queue = d.queue_d;
     p.rays = d.rays_d;
     p.t_out = t_out;
+    p.notify = notify;
+    p.done = d.queue_d + 1;
 
     const int bh = 8 >> ctx->hdr.fsaa;
     const unsigned int n_items = (unsigned int)n * ctx->hdr.tls_row
@@ -897,7 +957,17 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
 
-    QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
+    /* the work-item counter is not reset between launches: every warp of a
+     * launch draws until it is handed an item past the end, exactly once, so
+     * the counter ends at base + items + warps */
+    if (d.queue_base > 0x7F000000u)
+    {
+        QR_CUDA(ctx, cudaMemsetAsync(d.queue_d, 0, sizeof(unsigned int), d.stream));
+        d.queue_base = 0;
+    }
+    p.queue_base = d.queue_base;
+    p.n_warps = grid * warps;
+    d.queue_base += n_items + p.n_warps;
     if (first)
     {
         QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
@@ -939,13 +1009,89 @@ static int qr_collect_rays(qr_ctx *ctx)
     return QR_OK;
 }
 
-/* is "frame" page-locked by its owner (so the copy engine can write it)? */
-static bool qr_frame_pinned(uint32_t *frame)
+/* is the whole of [frame, frame + bytes) page-locked (so the copy engine or
+ * the kernel can write it)?  Both ends are asked: a buffer that grew at the
+ * same address is only partly registered */
+static bool qr_frame_pinned(const void *frame, size_t bytes)
 {
     cudaPointerAttributes at;
-    const bool yes = cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    bool yes = cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    if (yes && bytes > 1)
+    {
+        yes = cudaPointerGetAttributes(&at, (const uint8_t *)frame + bytes - 1) == cudaSuccess
+           && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
     return yes;
+}
+
+/*
+ * QR_B200_PIN_FRAME=1: page-lock the application's framebuffer (RooT's XShm
+ * image, core_test's frame) so the copy engine or the kernel writes it
+ * directly.  The registry remembers how much of each buffer it registered: a
+ * frame that grew, moved or changed its stride is registered again, the
+ * oldest entry makes room.  Returns whether [frame, frame + bytes) is
+ * page-locked now.
+ */
+static bool qr_pin_frame(qr_ctx *ctx, void *frame, size_t bytes)
+{
+    int slot = -1;
+    ctx->pin_clock++;
+    for (int k = 0; k < 4; k++)
+    {
+        if (ctx->pinned[k] == frame)
+        {
+            if (ctx->pinned_bytes[k] >= bytes)
+            {
+                ctx->pinned_age[k] = ctx->pin_clock;
+                return qr_frame_pinned(frame, bytes);
+            }
+            cudaHostUnregister(ctx->pinned[k]);         /* grew at the same address */
+            cudaGetLastError();
+            ctx->pinned[k] = NULL;
+            slot = k;
+        }
+    }
+    /* an entry that overlaps the new range is stale (its buffer was freed) */
+    for (int k = 0; k < 4; k++)
+    {
+        if (ctx->pinned[k] != NULL)
+        {
+            const uint8_t *a = (const uint8_t *)ctx->pinned[k], *b = (const uint8_t *)frame;
+            if (a < b + bytes && b < a + ctx->pinned_bytes[k])
+            {
+                cudaHostUnregister(ctx->pinned[k]);
+                cudaGetLastError();
+                ctx->pinned[k] = NULL;
+                if (slot < 0) slot = k;
+            }
+        }
+    }
+    for (int k = 0; k < 4 && slot < 0; k++)
+    {
+        if (ctx->pinned[k] == NULL) slot = k;
+    }
+    if (slot < 0)
+    {
+        slot = 0;
+        for (int k = 1; k < 4; k++)
+        {
+            if ((int)(ctx->pinned_age[k] - ctx->pinned_age[slot]) < 0) slot = k;
+        }
+        cudaHostUnregister(ctx->pinned[slot]);
+        cudaGetLastError();
+        ctx->pinned[slot] = NULL;
+    }
+    if (cudaHostRegister(frame, bytes, cudaHostRegisterDefault) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    ctx->pinned[slot] = frame;
+    ctx->pinned_bytes[slot] = bytes;
+    ctx->pinned_age[slot] = ctx->pin_clock;
+    return true;
 }
 
 /*
@@ -977,10 +1123,10 @@ static void qr_helper_main(qr_ctx *ctx, int k)
         /* the thread that starts the helpers is typically a worker pinned to
          * one core (root/RooT_linux.cpp:681-699); they must not share that
          * core with it */
-        cpu_set_t all;
-        CPU_ZERO(&all);
-        for (int i = 0; i < CPU_SETSIZE; i++) CPU_SET(i, &all);
-        sched_setaffinity(0, sizeof(all), &all);
+        /* ... nor escape the CPU set the process was given (taskset, cgroup
+         * pinning of a comparison run): the mask captured when the library
+         * was loaded, before any worker pinned itself */
+        if (g_load_affinity_ok) sched_setaffinity(0, sizeof(g_load_affinity), &g_load_affinity);
     }
     cudaSetDevice(ctx->dev[0].id);
     std::unique_lock<std::mutex> lk(ctx->hmtx);
@@ -1085,7 +1231,16 @@ static int qr_frame_ensure(qr_ctx *ctx)
     const size_t fbytes = (size_t)stride * h.y_res * sizeof(uint32_t);
     qr_dev &d0 = ctx->dev[0];
     QR_CUDA(ctx, cudaSetDevice(d0.id));
-    return qr_grow(ctx, (void **)&d0.frame_d, &d0.frame_cap, fbytes, false);
+    /* the frame is followed by QR_NOTIFY_SLOTS words of completion counters
+     * (qr_frame_notify_slot): zero when the buffer is (re)allocated */
+    const size_t need = fbytes + QR_NOTIFY_SLOTS * sizeof(uint32_t);
+    const bool fresh = d0.frame_cap < need;
+    int rc = qr_grow(ctx, (void **)&d0.frame_d, &d0.frame_cap, need, false);
+    if (rc == QR_OK && fresh)
+    {
+        QR_CUDA(ctx, cudaMemsetAsync((uint8_t *)d0.frame_d + fbytes, 0, QR_NOTIFY_SLOTS * sizeof(uint32_t), d0.stream));
+    }
+    return rc;
 }
 
 extern "C" int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, int y0, int y1)
@@ -1125,9 +1280,106 @@ extern "C" int qr_render_rows(qr_ctx *ctx, uint32_t *frame_dev, int stride, int 
     {
         return qr_fail(ctx, QR_E_ARG, "qr_render_rows: bad arguments");
     }
+    return qr_render_rows_notify(ctx, frame_dev, stride, tile_row0, tile_row_step, NULL);
+}
+
+extern "C" int qr_render_rows_notify(qr_ctx *ctx, uint32_t *frame_dev, int stride, int tile_row0,
+                                     int tile_row_step, uint32_t *notify_dev)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_render_rows: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    if (frame_dev == NULL || stride < h.x_res || tile_row0 < 0 || tile_row_step < 1)
+    {
+        return qr_fail(ctx, QR_E_ARG, "qr_render_rows: bad arguments");
+    }
     const int n = tile_row0 < h.tls_col ? (h.tls_col - tile_row0 + tile_row_step - 1) / tile_row_step : 0;
     for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
-    return qr_launch_rows(ctx, 0, frame_dev, stride, tile_row0, tile_row_step, n, NULL);
+    int rc = qr_launch_rows(ctx, 0, frame_dev, stride, tile_row0, tile_row_step, n, NULL, true,
+                            (unsigned int *)notify_dev);
+    if (rc == QR_OK && n <= 0 && notify_dev != NULL)
+    {
+        /* nothing to render for this rank: the signal is still owed */
+        qr_dev &d0 = ctx->dev[0];
+        qr_add_kernel<<<1, 1, 0, d0.stream>>>((unsigned int *)notify_dev);
+        QR_CUDA(ctx, cudaGetLastError());
+    }
+    if (rc == QR_OK && ctx->pipelined)
+    {
+        /* pipelined mode: the next upload into this scene slot waits for the
+         * kernels that read it */
+        qr_dev &d0 = ctx->dev[0];
+        if (d0.pipe_ev[ctx->slot] != NULL)
+        {
+            QR_CUDA(ctx, cudaEventRecord(d0.pipe_ev[ctx->slot], d0.stream));
+        }
+    }
+    return rc;
+}
+
+extern "C" int qr_wait_notify(qr_ctx *ctx, uint32_t *notify_dev, uint32_t target)
+{
+    if (ctx == NULL || notify_dev == NULL)
+    {
+        return QR_E_ARG;
+    }
+    qr_dev &d0 = ctx->dev[0];
+    QR_CUDA(ctx, cudaSetDevice(d0.id));
+    qr_wait_kernel<<<1, 1, 0, d0.stream>>>((unsigned int *)notify_dev, (unsigned int)target);
+    QR_CUDA(ctx, cudaGetLastError());
+    return QR_OK;
+}
+
+extern "C" int qr_host_register(qr_ctx *ctx, void *host, size_t bytes, uint32_t **dev_ptr)
+{
+    if (ctx == NULL || host == NULL || bytes == 0 || dev_ptr == NULL)
+    {
+        return QR_E_ARG;
+    }
+    QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    QR_CUDA(ctx, cudaHostRegister(host, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    void *d = NULL;
+    cudaError_t e = cudaHostGetDevicePointer(&d, host, 0);
+    if (e != cudaSuccess)
+    {
+        cudaHostUnregister(host);
+        QR_CUDA(ctx, e);
+    }
+    *dev_ptr = (uint32_t *)d;
+    return QR_OK;
+}
+
+extern "C" int qr_host_unregister(qr_ctx *ctx, void *host)
+{
+    if (ctx == NULL || host == NULL)
+    {
+        return QR_E_ARG;
+    }
+    QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+    QR_CUDA(ctx, cudaHostUnregister(host));
+    return QR_OK;
+}
+
+extern "C" int qr_frame_notify_slot(qr_ctx *ctx, uint32_t *frame_dev, int index, uint32_t **slot_dev)
+{
+    if (ctx == NULL || frame_dev == NULL || slot_dev == NULL || index < 0 || index >= QR_NOTIFY_SLOTS)
+    {
+        return QR_E_ARG;
+    }
+    if (!ctx->have_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_frame_notify_slot: no scene uploaded");
+    }
+    const qr_blob_header &h = ctx->hdr;
+    const int stride = h.x_row >= h.x_res ? h.x_row : h.x_res;
+    *slot_dev = frame_dev + (size_t)stride * h.y_res + (size_t)index;
+    return QR_OK;
 }
 
 /*
@@ -1234,30 +1486,11 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     bool direct = false;
     if (stride > 0)
     {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, frame) == cudaSuccess && at.type == cudaMemoryTypeHost)
-        {
-            direct = true;
-        }
-        cudaGetLastError();
+        const size_t ubytes = ((size_t)stride * (h.y_res - 1) + h.x_res) * sizeof(uint32_t);
+        direct = qr_frame_pinned(frame, ubytes);
         if (!direct && ctx->pin_frames)
         {
-            /* an application framebuffer lives as long as the scene: page-lock
-             * it once (RooT's XShm image, core_test's frame) */
-            for (int k = 0; k < 4 && !direct; k++)
-            {
-                if (ctx->pinned[k] == NULL)
-                {
-                    const size_t bytes = ((size_t)stride * (h.y_res - 1) + h.x_res) * sizeof(uint32_t);
-                    if (cudaHostRegister(frame, bytes, cudaHostRegisterDefault) == cudaSuccess)
-                    {
-                        ctx->pinned[k] = frame;
-                        direct = true;
-                    }
-                    cudaGetLastError();
-                    break;
-                }
-            }
+            direct = qr_pin_frame(ctx, frame, ubytes);
         }
     }
     if (!direct)
@@ -1510,26 +1743,12 @@ extern "C" int qr_render_fetch(qr_ctx *ctx, int ticket, uint32_t *frame, int str
     QR_CUDA(ctx, cudaSetDevice(d0.id));
     QR_CUDA(ctx, cudaStreamWaitEvent(d0.copy, d0.pipe_ev[ticket], 0));
 
-    bool direct = stride > 0 && qr_frame_pinned(frame);
+    const size_t ubytes = stride > 0 ? ((size_t)stride * (h.y_res - 1) + h.x_res) * sizeof(uint32_t) : 0;
+    bool direct = stride > 0 && qr_frame_pinned(frame, ubytes);
     if (!direct && stride > 0 && ctx->pin_frames)
     {
-        /* QR_B200_PIN_FRAME=1: an application framebuffer lives as long as the
-         * scene; page-lock it once (as qr_render does) and let the copy engine
-         * write it */
-        for (int k = 0; k < 4 && !direct; k++)
-        {
-            if (ctx->pinned[k] == NULL)
-            {
-                const size_t bytes = ((size_t)stride * (h.y_res - 1) + h.x_res) * sizeof(uint32_t);
-                if (cudaHostRegister(frame, bytes, cudaHostRegisterDefault) == cudaSuccess)
-                {
-                    ctx->pinned[k] = frame;
-                    direct = true;
-                }
-                cudaGetLastError();
-                break;
-            }
-        }
+        /* QR_B200_PIN_FRAME=1: let the copy engine write the application's frame */
+        direct = qr_pin_frame(ctx, frame, ubytes);
     }
     if (direct)
     {

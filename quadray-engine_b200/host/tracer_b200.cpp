@@ -29,6 +29,7 @@
 
 #include "tracer.h"
 #include "format.h"
+#include <mutex>
 #include "engine.h"
 
 #include "qr_flatten.h"
@@ -179,6 +180,13 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     {
         return;
     }
+
+    /* The reference's render0 is re-entrant per rt_SIMD_INFOX; here one GPU
+     * context, one flattener and (pipelined mode) one frame in flight serve the
+     * process.  Scenes of several rt_Platform instances that render
+     * concurrently take turns. */
+    static std::mutex g_render_mtx;
+    std::lock_guard<std::mutex> render_lock(g_render_mtx);
 
     qr_context();
 

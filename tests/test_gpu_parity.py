@@ -120,6 +120,29 @@ def test_gpu_stride_and_bottom_up_frames(entry, ctx):
     assert np.array_equal(flip[::-1], ref)
 
 
+def test_gpu_frames_need_no_16_byte_alignment(entry, pkg, ctx):
+    """Frame pointers at base + 4 / + 8 / + 12 bytes, device and page-locked
+    host (the zero-copy path writes the latter from the kernel): the 128-bit
+    pixel stores are chosen by address, so nothing faults and every pixel
+    arrives."""
+    import torch
+    blob, ref, _ = entry.load_golden("test05_odd")
+    h, w = ref.shape
+    ctx.upload(blob)
+    for off in (1, 2, 3):
+        for stride in (w, w + 5):
+            buf = torch.zeros(h * stride + 8, dtype=torch.int32, device="cuda:0")
+            torch.cuda.synchronize()
+            ctx.render_device(buf.data_ptr() + 4 * off, stride, 0, h)
+            ctx.sync()
+            got = buf.cpu().numpy().view(np.uint32)[off:off + h * stride].reshape(h, stride)[:, :w]
+            assert np.array_equal(got, ref), (off, stride)
+            host = torch.zeros(h * stride + 8, dtype=torch.int32).pin_memory()
+            view = host.numpy().view(np.uint32)[off:off + h * stride].reshape(h, stride)
+            ctx._check(ctx.lib.qr_render(ctx.h, view.ctypes.data, stride))
+            assert np.array_equal(view[:, :w], ref), (off, stride, "host")
+
+
 def test_gpu_render_device_bands(entry, pkg, ctx):
     """Tile-row bands rendered separately into a caller-owned device buffer
     assemble into the full frame (what one-process-per-GPU ranks do)."""
@@ -136,6 +159,43 @@ def test_gpu_render_device_bands(entry, pkg, ctx):
     ctx.sync()
     got = buf.cpu().numpy().view(np.uint32)
     assert np.array_equal(got, ref)
+
+
+def test_gpu_render_rows_notify_and_wait(entry, pkg, ctx):
+    """The collective-free completion signal of sharded frames: every "rank"
+    (here: three launches on one GPU) bumps the counter behind the library's
+    framebuffer from its kernel's last warp; the stream then waits for the
+    count.  The work-item queue is never reset between launches, so this also
+    checks that back-to-back launches hand out every item exactly once."""
+    import torch
+    blob, ref, _ = entry.load_golden("test05_odd")
+    h, w = ref.shape
+    ctx.upload(blob)
+    fptr, stride = ctx.frame_device()
+    slot = ctx.frame_notify_slot(fptr, 3)
+
+    class _Dev(object):
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False),
+                                             "version": 2}
+    cnt = torch.as_tensor(_Dev(slot, (1,)), device="cuda:0")
+    frame = torch.as_tensor(_Dev(fptr, (h, stride)), device="cuda:0")
+    cnt.zero_()
+    torch.cuda.synchronize()
+    for rep in range(1, 4):
+        frame.zero_()
+        torch.cuda.synchronize()
+        for r in range(3):
+            ctx.render_rows_notify(fptr, stride, r, 3, slot)
+        ctx.wait_notify(slot, 3 * rep)
+        ctx.sync()
+        assert int(cnt.item()) == 3 * rep
+        assert np.array_equal(frame.cpu().numpy().view(np.uint32)[:, :w], ref), rep
+    # a rank with no tile rows of its own still signals
+    ctx.render_rows_notify(fptr, stride, 10 ** 6, 1, slot)
+    ctx.wait_notify(slot, 10)
+    ctx.sync()
+    assert int(cnt.item()) == 10
 
 
 def test_gpu_render_rows_interleaved(entry, pkg, ctx):

@@ -3,8 +3,14 @@
 the file bench.py reads the dominant kernel's DRAM traffic from.
 usage: ncu_summary.py raw.csv out.json "<capture command / note>" """
 import csv
+import hashlib
 import json
+import os
+import re
+import subprocess
 import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 raw, out, note = sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ""
 rows = list(csv.reader(open(raw)))
@@ -31,7 +37,25 @@ def to_bytes(v, u):
 
 
 m = {k: {"value": d[k][0], "unit": d[k][1]} for k in KEYS if k in d}
-res = {"capture": note, "kernel": d.get("Kernel Name", ("", ""))[0], "metrics": m}
+# stamp: which kernel this is a capture of (bench.py refuses the traffic figure
+# when the sources or the launch shape it runs differ)
+hsh = hashlib.sha256()
+for f in ("csrc/qr_b200.cu", "csrc/qr_core.cuh", "csrc/qr_kscene.h"):
+    hsh.update(open(os.path.join(ROOT, "quadray-engine_b200", f), "rb").read())
+try:
+    commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stdout=subprocess.PIPE,
+                            check=True).stdout.decode().strip()
+    dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "quadray-engine_b200/csrc"],
+                           stdout=subprocess.PIPE, check=True).stdout.decode().strip()
+    if dirty:
+        commit += "+uncommitted kernel edits"
+except Exception:
+    commit = None
+kname = d.get("Kernel Name", ("", ""))[0]
+mm = re.search(r"<\(?(?:bool\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", kname)
+res = {"capture": note, "kernel": kname, "commit": commit, "kernel_source_sha256": hsh.hexdigest(),
+       "threads_per_cta": int(mm.group(2)) if mm else int(float(d.get("launch__block_size", ("0", ""))[0])),
+       "metrics": m}
 if "dram__bytes_read.sum" in d:
     res["dram_bytes_per_launch"] = to_bytes(*d["dram__bytes_read.sum"]) + to_bytes(*d["dram__bytes_write.sum"])
 json.dump(res, open(out, "w"), indent=1)
