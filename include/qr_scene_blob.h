@@ -83,7 +83,9 @@ typedef struct qr_blob_header
     uint32_t ctx_flags;       /* param[1]: RT_PROP_GAMMA or 0 */
     float    t_min;           /* cam->pov */
     float    org[3];
-    int32_t  pad1[3];
+    uint32_t off_bounds;      /* optional section (0 = absent): qr_bound per surface */
+    int32_t  n_bounds;        /* = n_surf when present */
+    int32_t  pad1[1];
 
     /* rt_SIMD_CAMERA, engine.cpp:3559-3584 */
     float    cam_t_max;       /* +inf */
@@ -192,6 +194,24 @@ typedef struct qr_elem
 
 #define QR_ELEM_WORDS 4
 
+/*
+ * Bounding-box vertices of a surface in world space = rt_BOUND::verts of the
+ * element's "temp" (core/engine/rtgeom.h:254-299), what rt_SceneThread::stile
+ * projects onto the tile buffer (core/engine/engine.cpp:1956-2128).  Present
+ * when the engine left the tiling to the backend (RT_OPTS_TILING off: every
+ * tile head is the camera list): the device then culls the list per tile
+ * itself.  n = 0: unbounded (covers every tile, engine.cpp:2097-2105);
+ * n = -1: surface not in the camera list.
+ */
+typedef struct qr_bound
+{
+    int32_t  n;
+    float    v[8][3];
+    int32_t  pad[3];
+} qr_bound;
+
+#define QR_BOUND_WORDS 28
+
 #ifdef __cplusplus
 }
 #endif
@@ -202,12 +222,14 @@ static_assert(sizeof(qr_surface)  == QR_SURF_WORDS * 4, "qr_surface size");
 static_assert(sizeof(qr_material) == QR_MAT_WORDS  * 4, "qr_material size");
 static_assert(sizeof(qr_light)    == QR_LGT_WORDS  * 4, "qr_light size");
 static_assert(sizeof(qr_elem)     == QR_ELEM_WORDS * 4, "qr_elem size");
+static_assert(sizeof(qr_bound)    == QR_BOUND_WORDS * 4, "qr_bound size");
 #else
 _Static_assert(sizeof(qr_blob_header) == 256, "qr_blob_header must be 64 words");
 _Static_assert(sizeof(qr_surface)  == QR_SURF_WORDS * 4, "qr_surface size");
 _Static_assert(sizeof(qr_material) == QR_MAT_WORDS  * 4, "qr_material size");
 _Static_assert(sizeof(qr_light)    == QR_LGT_WORDS  * 4, "qr_light size");
 _Static_assert(sizeof(qr_elem)     == QR_ELEM_WORDS * 4, "qr_elem size");
+_Static_assert(sizeof(qr_bound)    == QR_BOUND_WORDS * 4, "qr_bound size");
 #endif
 
 #endif /* QR_SCENE_BLOB_H */

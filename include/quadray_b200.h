@@ -226,6 +226,8 @@ typedef struct qr_kernel_info
     int smem_static_bytes;
     int smem_dynamic_bytes;   /* for the currently uploaded scene, 0 if none */
     int scene_in_smem;        /* 1 when surfaces/materials/lights are staged */
+    int device_tiling;        /* 1 when the tile lists of the current scene were built on the device
+                                 (the engine ran with RT_OPTS_TILING off and the blob carries bounds) */
 } qr_kernel_info;
 
 int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info);

@@ -42,7 +42,7 @@ class KernelInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in (
         "sm_count", "threads_per_cta", "ctas_per_sm", "regs_per_thread",
         "local_bytes_per_thread", "smem_static_bytes", "smem_dynamic_bytes",
-        "scene_in_smem")]
+        "scene_in_smem", "device_tiling")]
 
 
 _lib = None

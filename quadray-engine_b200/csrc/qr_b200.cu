@@ -34,6 +34,7 @@
 
 #include "quadray_b200.h"
 #include "qr_core.cuh"
+#include "qr_tiling.cuh"
 
 /*
  * Launch shapes (threads per CTA, resident CTAs per SM the register budget is
@@ -336,6 +337,37 @@ qr_render_kernel(const qr_launch p)
     }
 }
 
+/*
+ * Device-side tiling (qr_tiling.cuh), two launches per uploaded scene: the
+ * tile rectangle of every leaf of the camera list, then one list per tile.
+ */
+__global__ void qr_tile_rect_kernel(uint8_t *img)
+{
+    const qr_blob_header *h = (const qr_blob_header *)img;
+    const uint32_t n = (uint32_t)h->pad3[2];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const qr_kleaf *leaf = (const qr_kleaf *)(img + (uint32_t)h->pad3[1]);
+    const qr_bound *bnd = (const qr_bound *)(img + h->off_bounds);
+    qr_tile_rect_t *rect = (qr_tile_rect_t *)(img + (uint32_t)h->pad3[3]);
+    rect[i] = qr_tile_rect(*h, bnd[leaf[i].bound]);
+}
+
+__global__ void qr_tile_list_kernel(uint8_t *img)
+{
+    const qr_blob_header *h = (const qr_blob_header *)img;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)h->n_tiles) return;
+    const qr_kleaf *leaf = (const qr_kleaf *)(img + (uint32_t)h->pad3[1]);
+    const qr_tile_rect_t *rect = (const qr_tile_rect_t *)(img + (uint32_t)h->pad3[3]);
+    const uint32_t cap = (uint32_t)h->pad0[1];
+    const uint32_t first = ((uint32_t)h->pad0[0] - h->off_elem) / (uint32_t)sizeof(qr_kelem) + t * cap;
+    qr_kelem *out = (qr_kelem *)(img + h->off_elem) + first;
+    qr_tile_list_build(leaf, (uint32_t)h->pad3[2], rect, (int32_t)(t % (uint32_t)h->tls_row),
+                       (int32_t)(t / (uint32_t)h->tls_row), out);
+    ((int32_t *)(img + h->off_tiles))[t] = (int32_t)first;
+}
+
 /* a rank without rows of its own still owes its completion signal */
 __global__ void qr_add_kernel(unsigned int *flag)
 {
@@ -455,6 +487,7 @@ struct qr_ctx
     size_t          pinned_bytes[4];/* ... and how much of them */
     unsigned        pinned_age[4];  /* last use (the oldest entry is evicted) */
     unsigned        pin_clock;
+    bool            device_tiling;  /* the current scene's tile lists were built on the device */
     int             pipelined;      /* qr_pipeline(ctx, 1): scenes alternate between two slots */
     int             slot;           /* slot of the current scene */
     bool            pending[2];     /* a frame begun in this slot has not been collected */
@@ -840,7 +873,7 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
     {
         qr_dev &d = ctx->dev[i];
         QR_CUDA(ctx, cudaSetDevice(d.id));
-        rc = qr_grow(ctx, (void **)&d.blob_d[sl], &d.blob_cap[sl], n, false);
+        rc = qr_grow(ctx, (void **)&d.blob_d[sl], &d.blob_cap[sl], pk.device_bytes(), false);
         if (rc != QR_OK)
         {
             return rc;
@@ -857,7 +890,17 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         {
             QR_CUDA(ctx, cudaMemcpyAsync(d.blob_d[sl], d0.blob_h[sl], n, cudaMemcpyHostToDevice, d.stream));
         }
+        if (pk.device_tiling())
+        {
+            /* the engine left the tiling to us: tile rectangles of the camera
+             * list's leaves, then one list per tile, ahead of the frame's kernels */
+            const unsigned int nl = (unsigned int)kh->pad3[2], nt = (unsigned int)kh->n_tiles;
+            qr_tile_rect_kernel<<<(nl + 127) / 128, 128, 0, d.stream>>>(d.blob_d[sl]);
+            qr_tile_list_kernel<<<(nt + 127) / 128, 128, 0, d.stream>>>(d.blob_d[sl]);
+            QR_CUDA(ctx, cudaGetLastError());
+        }
     }
+    ctx->device_tiling = pk.device_tiling();
 
     ctx->hdr = *h;
 
@@ -2054,5 +2097,6 @@ extern "C" int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info)
     info->smem_static_bytes = (int)ctx->fattr.sharedSizeBytes;
     info->smem_dynamic_bytes = (int)ctx->stage_bytes + g_shapes[ctx->shape].threads * QR_SC_QUADS * 16;
     info->scene_in_smem = ctx->stage_bytes != 0;
+    info->device_tiling = ctx->have_scene && ctx->device_tiling ? 1 : 0;
     return QR_OK;
 }

@@ -103,6 +103,24 @@ struct alignas(8) qr_kelem { uint32_t w; int32_t aux; };
 #define QR_KF_OWN       64u /* quadric / two-plane: its own matrix, outside any node */
 #define QR_K_SURF_OFF(w) ((w) & ~127u)  /* byte offset of the surface record (128 B each) */
 
+/*
+ * Device-side tiling (qr_tiling.cuh): when the engine left the tiling to the
+ * backend, the camera list's leaves are tabled here, in list order, with the
+ * transform node they sit in; the device writes one compiled list per tile
+ * from them.  Image sections behind the texels:
+ *   kleaf table | qr_bound per surface | tile rectangle per leaf (device) || tile lists (device, not uploaded)
+ * header: pad3[1] = off_kleaf, pad3[2] = n_kleaf, pad3[3] = off_rects,
+ *         pad0[0] = off_tlists, pad0[1] = elements per tile list (capacity)
+ */
+#if defined(__CUDACC__)
+struct __align__(16) qr_kleaf { uint32_t w; int32_t aux; uint32_t open; uint32_t bound; };
+#else
+struct alignas(16) qr_kleaf { uint32_t w; int32_t aux; uint32_t open; uint32_t bound; };
+#endif
+#define QR_KLEAF_NO_NODE  0xFFFFFFFFu   /* open: record offset of the leaf's open node, or none */
+#define QR_KTILE_MAX_LEAVES   8192u     /* beyond: the untiled list is walked (bounding volumes cull) */
+#define QR_KTILE_MAX_BYTES    (1536ull << 20)
+
 #define QR_KC_NEG        1u /* clip lists: rt_ELEM.data < 0 (inner side / accum enter) */
 #define QR_KC_ACCUM      2u /* clip lists: accum marker (no surface) */
 
@@ -285,11 +303,36 @@ class qr_kpacker
         k.n_elem = (int32_t)out.size();
         k.off_tiles = off;  off = qr_k_align16(off + (uint32_t)h->n_tiles * sizeof(int32_t));
         k.off_texels = off; off = qr_k_align16(off + (uint32_t)h->n_texels * sizeof(uint32_t));
+        k.off_bounds = 0; k.n_bounds = 0;
+        k.pad0[0] = 0; k.pad0[1] = 0; k.pad3[1] = 0; k.pad3[2] = 0; k.pad3[3] = 0;
+        dev_bytes = off;
+
+        /* device-side tiling: the engine left every tile head at the camera
+         * list and sent the bounding boxes along */
+        leaves.clear();
+        if (plan_tiling())
+        {
+            k.pad3[1] = (int32_t)off; off = qr_k_align16(off + (uint32_t)(leaves.size() * sizeof(qr_kleaf)));
+            k.pad3[2] = (int32_t)leaves.size();
+            k.off_bounds = off;       off = qr_k_align16(off + (uint32_t)h->n_bounds * (uint32_t)sizeof(qr_bound));
+            k.n_bounds = h->n_bounds;
+            k.pad3[3] = (int32_t)off; off = qr_k_align16(off + (uint32_t)(leaves.size() * 16u));
+            k.pad0[0] = (int32_t)off;
+            k.pad0[1] = (int32_t)tile_cap;
+            dev_bytes = (size_t)off + (size_t)h->n_tiles * tile_cap * sizeof(qr_kelem);
+        }
         k.total_bytes = off;
         return 0;
     }
 
+    /* bytes of the image that are written here and copied to the device */
     size_t bytes() const { return k.total_bytes; }
+
+    /* bytes the device buffer needs: the image plus the tile lists the device writes */
+    size_t device_bytes() const { return dev_bytes; }
+
+    /* does the device build the tile lists (qr_tiling.cuh)? */
+    bool device_tiling() const { return !leaves.empty(); }
 
     /* offset of the list elements = size of the part staged in shared memory */
     uint32_t prefix_bytes() const { return k.off_elem; }
@@ -375,11 +418,75 @@ class qr_kpacker
         memcpy(o + k.off_elem, out.data(), out.size() * sizeof(qr_kelem));
         memcpy(o + k.off_tiles, k_tiles.data(), (size_t)h->n_tiles * sizeof(int32_t));
         memcpy(o + k.off_texels, blob + h->off_texels, (size_t)h->n_texels * sizeof(uint32_t));
+        if (!leaves.empty())
+        {
+            memcpy(o + (uint32_t)k.pad3[1], leaves.data(), leaves.size() * sizeof(qr_kleaf));
+            memcpy(o + k.off_bounds, blob + h->off_bounds, (size_t)h->n_bounds * sizeof(qr_bound));
+            memset(o + (uint32_t)k.pad3[3], 0, leaves.size() * 16u);
+        }
     }
 
     private:
 
     static qr_kelem make(uint32_t w, int32_t aux) { qr_kelem e; e.w = w; e.aux = aux; return e; }
+
+    /*
+     * Device-side tiling applies when the blob carries bounding boxes and every
+     * tile head is the same list (the camera list): table its leaves with the
+     * node each one sits in, by walking the COMPILED list -- bounding-volume
+     * elements are dropped as the reference's tile lists drop them
+     * (engine.cpp:3160-3167), OPEN / CLOSE become the leaf's "open" field.
+     */
+    bool plan_tiling()
+    {
+        if (h->off_bounds == 0 || h->n_bounds != h->n_surf || h->n_tiles < 2) return false;
+        if ((uint64_t)h->off_bounds + (uint64_t)h->n_bounds * sizeof(qr_bound) > h->total_bytes) return false;
+        for (int t = 1; t < h->n_tiles; t++)
+        {
+            if (tl[t] != tl[0]) return false;
+        }
+        if (k_tiles[0] <= 0) return false;
+        uint32_t open = QR_KLEAF_NO_NODE;
+        size_t guard = 0;
+        for (size_t i = (size_t)k_tiles[0]; ; )
+        {
+            if (i >= out.size() || guard++ > out.size()) { leaves.clear(); return false; }
+            const qr_kelem e = out[i];
+            const uint32_t kind = QR_K_KIND(e.w);
+            if (e.w == QR_KEND) break;
+            if (kind == QR_K_JUMP) { i = (size_t)((int64_t)i + e.aux / (int32_t)sizeof(qr_kelem)); continue; }
+            if (kind == QR_K_OPEN)  open = QR_K_SURF_OFF(e.w);
+            else
+            if (kind == QR_K_CLOSE) open = QR_KLEAF_NO_NODE;
+            else
+            if (kind != QR_K_BV && kind != QR_K_NOP)
+            {
+                qr_kleaf lf;
+                lf.w = e.w; lf.aux = e.aux;
+                lf.open = (e.w & QR_KF_NODE) ? open : QR_KLEAF_NO_NODE;
+                lf.bound = QR_K_SURF_OFF(e.w) >> 7;
+                const uint32_t kd = kind;
+                const bool own = kd == QR_K_PLANE_G || ((kd == QR_K_QUADRIC || kd == QR_K_TWOPLANE) && (e.w & QR_KF_OWN));
+                if (own) lf.open = QR_KLEAF_NO_NODE;
+                leaves.push_back(lf);
+            }
+            i++;
+        }
+        if (leaves.empty() || leaves.size() > QR_KTILE_MAX_LEAVES) { leaves.clear(); return false; }
+        /* elements a tile list can need: its leaves, an OPEN and a CLOSE per run
+         * of leaves of one node (a sub-sequence never has more runs), a CLOSE
+         * per leaf with its own matrix, the END */
+        size_t runs = 0, own = 0;
+        for (size_t i = 0; i < leaves.size(); i++)
+        {
+            if (leaves[i].open != QR_KLEAF_NO_NODE && (i == 0 || leaves[i].open != leaves[i - 1].open)) runs++;
+            const uint32_t kd = QR_K_KIND(leaves[i].w);
+            if (kd == QR_K_PLANE_G || ((kd == QR_K_QUADRIC || kd == QR_K_TWOPLANE) && (leaves[i].w & QR_KF_OWN))) own++;
+        }
+        tile_cap = (uint32_t)(leaves.size() + 2 * runs + own + 1);
+        if ((uint64_t)h->n_tiles * tile_cap * sizeof(qr_kelem) > QR_KTILE_MAX_BYTES) { leaves.clear(); return false; }
+        return true;
+    }
 
     /* index of a blob material in the deduplicated table */
     int32_t kmat_of(int32_t m) const
@@ -573,6 +680,9 @@ class qr_kpacker
     std::vector<int32_t>  mat_map, mat_uniq;            /* blob material -> table index, table index -> blob material */
     std::unordered_map<uint64_t, std::vector<int32_t> > mat_bucket;
     std::vector<qr_kelem> out;
+    std::vector<qr_kleaf> leaves;                       /* camera list's leaves (device tiling), or empty */
+    uint32_t              tile_cap;
+    size_t                dev_bytes;
     std::vector<qr_kfix>  fix;
     std::unordered_map<int32_t, int32_t> heads;
 };

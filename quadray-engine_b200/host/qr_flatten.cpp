@@ -16,6 +16,7 @@
  */
 
 #include <string.h>
+#include <utility>
 
 #include "tracer.h"
 #include "format.h"
@@ -401,7 +402,53 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
         }
         tiles[t] = list_head(tl[t], LIST_SURF);
     }
+
+    /* RT_OPTS_TILING off: every tile head is the camera list
+     * (engine.cpp:3236-3248).  The bounding boxes the engine's stile() would
+     * have projected travel with the blob, and the device culls per tile. */
+    bool untiled = n_tiles > 1 && tl[0] != RT_NULL;
+    for (int32_t t = 1; t < n_tiles && untiled; t++)
+    {
+        untiled = tl[t] == tl[0];
+    }
+    std::vector<std::pair<int32_t, const rt_BOUND *> > clist_bounds;
+    if (untiled)
+    {
+        for (const rt_ELEM *e = tl[0]; e != RT_NULL; e = e->next)
+        {
+            const rt_SIMD_SURFACE *s = (const rt_SIMD_SURFACE *)e->simd;
+            if (s == RT_NULL || e->temp == RT_NULL)
+            {
+                untiled = false;
+                break;
+            }
+            clist_bounds.push_back(std::make_pair(surface(s), (const rt_BOUND *)e->temp));
+        }
+    }
     drain();
+
+    bounds.clear();
+    if (untiled)
+    {
+        qr_bound none;
+        memset(&none, 0, sizeof(none));
+        none.n = -1;
+        bounds.assign(surfs.size(), none);
+        for (size_t i = 0; i < clist_bounds.size(); i++)
+        {
+            const rt_BOUND *b = clist_bounds[i].second;
+            qr_bound &r = bounds[(size_t)clist_bounds[i].first];
+            /* more vertices than a box has: treated as unbounded */
+            r.n = b->verts_num >= 0 && b->verts_num <= 8 && (b->verts != RT_NULL || b->verts_num == 0)
+                ? (int32_t)b->verts_num : 0;
+            for (int k = 0; k < r.n; k++)
+            {
+                r.v[k][0] = b->verts[k].pos[RT_X];
+                r.v[k][1] = b->verts[k].pos[RT_Y];
+                r.v[k][2] = b->verts[k].pos[RT_Z];
+            }
+        }
+    }
 
     h.n_surf   = (int32_t)surfs.size();
     h.n_mat    = (int32_t)mats.size();
@@ -417,6 +464,12 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     h.off_elem   = off; off = align16(off + h.n_elem   * sizeof(qr_elem));
     h.off_tiles  = off; off = align16(off + h.n_tiles  * sizeof(int32_t));
     h.off_texels = off; off = align16(off + h.n_texels * sizeof(uint32_t));
+    if (!bounds.empty())
+    {
+        h.off_bounds = off;
+        h.n_bounds = (int32_t)bounds.size();
+        off = align16(off + (uint32_t)(bounds.size() * sizeof(qr_bound)));
+    }
     h.total_bytes = off;
 
     blob.resize(off);
@@ -429,7 +482,8 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
             h.off_elem   + h.n_elem   * (uint32_t)sizeof(qr_elem),
             h.off_tiles  + h.n_tiles  * (uint32_t)sizeof(int32_t),
             h.off_texels + h.n_texels * (uint32_t)sizeof(uint32_t) };
-        const uint32_t nexts[7] = { h.off_surf, h.off_mat, h.off_lgt, h.off_elem, h.off_tiles, h.off_texels, off };
+        const uint32_t nexts[7] = { h.off_surf, h.off_mat, h.off_lgt, h.off_elem, h.off_tiles, h.off_texels,
+                                    h.n_bounds ? h.off_bounds : off };
         for (int k = 0; k < 7; k++)
         {
             if (nexts[k] > ends[k]) memset(&blob[ends[k]], 0, nexts[k] - ends[k]);
@@ -442,6 +496,7 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     if (h.n_elem)   memcpy(&blob[h.off_elem],   &elems[0],  h.n_elem   * sizeof(qr_elem));
     if (h.n_tiles)  memcpy(&blob[h.off_tiles],  &tiles[0],  h.n_tiles  * sizeof(int32_t));
     if (h.n_texels) memcpy(&blob[h.off_texels], &texels[0], h.n_texels * sizeof(uint32_t));
+    if (h.n_bounds) memcpy(&blob[h.off_bounds], &bounds[0], bounds.size() * sizeof(qr_bound));
 
     *bytes = blob.size();
     return &blob[0];

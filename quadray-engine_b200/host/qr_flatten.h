@@ -140,6 +140,7 @@ class qr_Flattener
     std::vector<qr_light>       lgts;
     std::vector<uint32_t>       texels;
     std::vector<int32_t>        tiles;
+    std::vector<qr_bound>       bounds;         /* per surface, when the engine left the tiling to us */
     std::vector<uint8_t>        blob;
     size_t                      surf_done;
 };

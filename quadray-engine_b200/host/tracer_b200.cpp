@@ -220,6 +220,20 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
         qr_throw("B200 scene upload failed", g_ctx);
     }
     const double t2 = timing ? qr_now_ms() : 0.0;
+    {
+        /* QR_B200_EXPECT_DEVICE_TILING=1 (tests): the application runs the
+         * engine with RT_OPTS_TILING off and expects the tile lists to be
+         * built on the device */
+        static const bool expect = getenv("QR_B200_EXPECT_DEVICE_TILING") != RT_NULL;
+        if (expect)
+        {
+            qr_kernel_info ki;
+            if (qr_kernel_query(g_ctx, &ki) != QR_OK || !ki.device_tiling)
+            {
+                throw rt_Exception("B200 backend: device-side tiling expected, but the scene came tiled by the engine");
+            }
+        }
+    }
     if (g_pipelined)
     {
         /*

@@ -12,6 +12,46 @@
 #define QR_COUNT_OPS
 unsigned long long qr_ops[4] = {0, 0, 0, 0};
 #include "qr_core.cuh"
+#include "qr_tiling.cuh"
+
+/* device-tiling emulation: tiles built / elements written since the last call */
+static uint64_t qr_tiling_tiles = 0, qr_tiling_elems = 0;
+extern "C" void qr_hostsim_tiling(uint64_t out[2])
+{
+    out[0] = qr_tiling_tiles; out[1] = qr_tiling_elems;
+    qr_tiling_tiles = qr_tiling_elems = 0;
+}
+
+/*
+ * Surfaces (blob indices) of the list the device-side tiling builds for tile
+ * "tile" of an untiled blob, in list order; -1 when the blob does not qualify.
+ */
+extern "C" int qr_hostsim_tile_list(const void *blob, size_t bytes, int tile, int32_t *surf_out, int cap)
+{
+    const qr_blob_header *h = (const qr_blob_header *)blob;
+    if (bytes < sizeof(*h) || h->magic != QR_BLOB_MAGIC || h->total_bytes > bytes) return -1;
+    qr_kpacker pk;
+    if (pk.plan(blob) != 0 || !pk.device_tiling() || tile < 0 || tile >= h->n_tiles) return -1;
+    std::vector<uint8_t> img((pk.bytes() + 63) & ~(size_t)63);
+    pk.write(img.data());
+    const qr_blob_header *kh = (const qr_blob_header *)img.data();
+    const qr_kleaf *leaf = (const qr_kleaf *)(img.data() + (uint32_t)kh->pad3[1]);
+    const qr_bound *bnd = (const qr_bound *)(img.data() + kh->off_bounds);
+    const uint32_t nl = (uint32_t)kh->pad3[2];
+    std::vector<qr_tile_rect_t> rect(nl);
+    for (uint32_t i = 0; i < nl; i++) rect[i] = qr_tile_rect(*kh, bnd[leaf[i].bound]);
+    std::vector<qr_kelem> out((size_t)kh->pad0[1]);
+    const uint32_t n = qr_tile_list_build(leaf, nl, rect.data(), tile % kh->tls_row, tile / kh->tls_row, out.data());
+    int m = 0;
+    for (uint32_t i = 0; i < n; i++)
+    {
+        const uint32_t kind = QR_K_KIND(out[i].w);
+        if (out[i].w == QR_KEND || kind == QR_K_OPEN || kind == QR_K_CLOSE) continue;
+        if (m < cap) surf_out[m] = (int32_t)(QR_K_SURF_OFF(out[i].w) >> 7);
+        m++;
+    }
+    return m;
+}
 
 /* algorithmic IEEE op counts since the last call: add/sub, mul, div, sqrt */
 extern "C" void qr_hostsim_ops(uint64_t out[4])
@@ -30,10 +70,32 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     /* the product path: blob -> packed kscene image (qr_kscene.h) -> core */
     qr_kpacker pk;
     if (pk.plan(blob) != 0) return -4;
-    const size_t kbytes = pk.bytes();
+    const size_t kbytes = pk.device_bytes();
     void *kimg = aligned_alloc(64, (kbytes + 63) & ~(size_t)63);
     if (kimg == NULL) return -3;
     pk.write(kimg);
+    if (pk.device_tiling())
+    {
+        /* what qr_tile_rect_kernel / qr_tile_list_kernel do on the device */
+        uint8_t *img = (uint8_t *)kimg;
+        const qr_blob_header *kh = (const qr_blob_header *)img;
+        const qr_kleaf *leaf = (const qr_kleaf *)(img + (uint32_t)kh->pad3[1]);
+        const qr_bound *bnd = (const qr_bound *)(img + kh->off_bounds);
+        qr_tile_rect_t *rect = (qr_tile_rect_t *)(img + (uint32_t)kh->pad3[3]);
+        const uint32_t nl = (uint32_t)kh->pad3[2], cap = (uint32_t)kh->pad0[1];
+        for (uint32_t i = 0; i < nl; i++) rect[i] = qr_tile_rect(*kh, bnd[leaf[i].bound]);
+        for (uint32_t t = 0; t < (uint32_t)kh->n_tiles; t++)
+        {
+            const uint32_t first = ((uint32_t)kh->pad0[0] - kh->off_elem) / (uint32_t)sizeof(qr_kelem) + t * cap;
+            const uint32_t n = qr_tile_list_build(leaf, nl, rect, (int32_t)(t % (uint32_t)kh->tls_row),
+                                                  (int32_t)(t / (uint32_t)kh->tls_row),
+                                                  (qr_kelem *)(img + kh->off_elem) + first);
+            if (n > cap) { free(kimg); return -5; }
+            ((int32_t *)(img + kh->off_tiles))[t] = (int32_t)first;
+            qr_tiling_elems += n;
+        }
+        qr_tiling_tiles += (uint64_t)kh->n_tiles;
+    }
     qr_view<false> v;
     qr_view_init(v, kimg);
 

@@ -50,6 +50,22 @@ def test_scene_api_renders_the_reference_frame(entry, tmp_path, name):
 
 
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
+@pytest.mark.parametrize("name", ["demo03_a4g_nt", "demo02_a4g_nt", "test14_full_nt", "test16_a4rg_nt", "test05_odd_nt"])
+def test_scene_api_with_device_side_tiling(entry, tmp_path, name):
+    """the application switches the engine's host tiling off
+    (RT_OPTS_TILING), the flattener sends the bounding boxes along and the
+    device builds the tile lists; the frame is the one the reference renders
+    with ITS tiling on.  Synchronous and pipelined."""
+    _, ref, meta = entry.load_golden(name)
+    env = {"QR_B200_EXPECT_DEVICE_TILING": "1"}
+    frame, _ = run_harness(meta["blob_args"].split(), tmp_path, env)
+    assert int((frame != ref).sum()) == 0, meta["blob_args"]
+    env["QR_B200_PIPELINE"] = "1"
+    frame, _ = run_harness(meta["blob_args"].split() + ["-t", "4", "-f", "3", "-d", "0"], tmp_path, env)
+    assert int((frame != ref).sum()) == 0, meta["blob_args"]
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="build/qr_b200_harness was not built")
 @pytest.mark.parametrize("name", GOLDEN_CRC)
 def test_generated_quadric_clouds_at_size(entry, tmp_path, name):
     """BASELINE.json config 5: 10k / 100k random quadrics under 8-ary

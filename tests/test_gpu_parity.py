@@ -56,6 +56,21 @@ def test_gpu_full_size_frames_vs_reference(entry, ctx, name):
     assert bad.size == 0, (meta["args"], bad[:10].tolist())
 
 
+def test_gpu_device_side_tiling_is_used_for_untiled_blobs(entry, ctx):
+    """Blobs flattened from an engine that ran with RT_OPTS_TILING off carry
+    bounding boxes: the library builds the tile lists on the device
+    (qr_tiling.cuh) and the frame is the reference's (rendered with the
+    engine's own host tiling)."""
+    blob, ref, _ = entry.load_golden("demo03_a4g_nt")
+    ctx.upload(blob)
+    assert ctx.kernel_info()["device_tiling"] == 1
+    assert np.array_equal(ctx.render_frame(), ref)
+    blob, ref, _ = entry.load_golden("demo03_a4g")
+    ctx.upload(blob)
+    assert ctx.kernel_info()["device_tiling"] == 0
+    assert np.array_equal(ctx.render_frame(), ref)
+
+
 def test_gpu_scene_staged_in_shared_memory(entry, ctx):
     blob, _, _ = entry.load_golden("demo03_a4g")
     ctx.upload(blob)

@@ -15,6 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "qr_ref_harness")
 B200 = os.path.join(ROOT, "build", "qr_b200_harness")
+NOTILE = "0x0230FFB9"       # RT_OPTS_FULL without RT_OPTS_TILING | RT_OPTS_TILING_EXT1
 
 
 def run(binary, args, env=None):
@@ -37,6 +38,12 @@ def main():
         ("b200_sync_%dthr" % ncpu, B200, ["-t", str(ncpu)], {}),
         ("b200_pipelined_1thr", B200, [], {"QR_B200_PIPELINE": "1"}),
         ("b200_pipelined_%dthr" % ncpu, B200, ["-t", str(ncpu)], {"QR_B200_PIPELINE": "1"}),
+        # engine tiling off (RT_OPTS_TILING / _EXT1 cleared), tile lists built on the device
+        ("b200_sync_%dthr_device_tiling" % ncpu, B200, ["-t", str(ncpu), "-p", NOTILE],
+         {"QR_B200_EXPECT_DEVICE_TILING": "1"}),
+        ("b200_pipelined_%dthr_device_tiling" % ncpu, B200, ["-t", str(ncpu), "-p", NOTILE],
+         {"QR_B200_PIPELINE": "1", "QR_B200_EXPECT_DEVICE_TILING": "1"}),
+        ("reference_%dthr_tiling_off" % ncpu, REF, ["-t", str(ncpu), "-p", NOTILE], {}),
     ]
     for name, binary, extra, env in cases:
         if not os.path.exists(binary):

@@ -66,6 +66,25 @@ CASES.update({
 })
 
 
+# Device-side tiling: the BLOB comes from the engine with
+# RT_OPTS_TILING off (every tile head is the camera list, bounding boxes sent
+# along, "_nt"), the FRAME from the reference with its own host tiling on.
+NOTILE = " -p 0x0230FFB9"       # RT_OPTS_FULL without TILING / TILING_EXT1
+CASES_NT = {
+    "demo01_a4g_nt":     "-s demo01 -a 2 -g",
+    "demo02_a4g_nt":     "-s demo02 -a 2 -g",
+    "demo03_a4g_nt":     "-s demo03 -a 2 -g -b 1000",
+    "test05_odd_nt":     "-s test05 -x 403 -y 250 -a 2",
+    "test12_full_nt":    "-s test12",
+    "test14_full_nt":    "-s test14",
+    "test15_a2_nt":      "-s test15 -a 1",
+    "test16_a4rg_nt":    "-s test16 -a 2 -r -g",
+    "test17_a4_nt":      "-s test17 -a 2",
+}
+CASES.update({k: v + " -p full" for k, v in CASES_NT.items()})
+BLOB_ARGS = {k: v + NOTILE for k, v in CASES_NT.items()}
+
+
 # Full-size cases (BASELINE.json configs 3 and 4): the reference frame is kept
 # as per-row CRC-32s instead of pixels ("h" suffix) so the fixtures stay small.
 CASES_HASHED = {
@@ -90,7 +109,12 @@ CASES_HASHED = {
     "demo01_1080p_a4rgh": "-s demo01 -x 1920 -y 1080 -a 2 -r -g",
     "demo02_1080p_a4rgh": "-s demo02 -x 1920 -y 1080 -a 2 -r -g",
     "demo03_1080p_a4rgh": "-s demo03 -x 1920 -y 1080 -a 2 -r -g",
+    # device-side tiling at the bench resolution and at 4K
+    "demo03_1080p_a4g_nth": "-s demo03 -x 1920 -y 1080 -a 2 -g -p full",
+    "demo03_4k_a4g_nth":    "-s demo03 -x 3840 -y 2160 -a 2 -g -p full",
 }
+BLOB_ARGS.update({"demo03_1080p_a4g_nth": "-s demo03 -x 1920 -y 1080 -a 2 -g" + NOTILE,
+                  "demo03_4k_a4g_nth": "-s demo03 -x 3840 -y 2160 -a 2 -g" + NOTILE})
 
 
 # Config 5 at size: only the reference frame's row CRC-32s are kept ("c"
@@ -168,12 +192,15 @@ def main_hashed(names):
             rf, of, bf = (os.path.join(td, n) for n in ("r.raw", "o.raw", "s.blob"))
             jr = run([REF] + args + ["-o", rf])
             # the oracle harness only has to flatten: one row is enough
-            run([ORC] + args + ["-o", of], {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_ROWS": "1"})
+            run([ORC] + BLOB_ARGS.get(name, CASES_HASHED[name]).split() + ["-o", of],
+                {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_ROWS": "1"})
             w, h = jr["x_res"], jr["y_res"]
             frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
             blob = np.fromfile(bf, dtype=np.uint8)
         meta = {"name": name, "args": CASES_HASHED[name], "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
                 "opts": jr["opts"], "ref_simd": jr["simd"]}
+        if name in BLOB_ARGS:
+            meta["blob_args"] = BLOB_ARGS[name]
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, blob=blob, rowcrc=row_crcs(frame),
                             meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
@@ -216,7 +243,7 @@ def main(names):
         with tempfile.TemporaryDirectory() as td:
             rf, of, bf, sf = (os.path.join(td, n) for n in ("r.raw", "o.raw", "s.blob", "st.json"))
             jr = run([REF] + args + ["-o", rf])
-            jo = run([ORC] + args + ["-o", of],
+            jo = run([ORC] + BLOB_ARGS.get(name, CASES[name]).split() + ["-o", of],
                      {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "1", "QR_ORACLE_STATS": sf})
             w, h = jr["x_res"], jr["y_res"]
             frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
@@ -233,6 +260,8 @@ def main(names):
             "rays": rays,           # shade-once algorithm (what the GPU casts)
             "ieee_ops": ops,        # algorithmic IEEE fp32 operations per frame
         }
+        if name in BLOB_ARGS:
+            meta["blob_args"] = BLOB_ARGS[name]
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, blob=blob, frame=frame, meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
         print("%-20s %4dx%-4d blob %7d B  npz %7d B  oracle(packet=1) != ref: %d px"

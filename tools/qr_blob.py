@@ -9,7 +9,7 @@ _HDR_FMT = "<4I" + "12i" + "I4f3i" + "f3f3f3f4f4f3ffIi" + "iIiIiIiIiIiI4i"
 _HDR_NAMES = (
     ["magic", "version", "total_bytes", "flags"]
     + ["x_res", "y_res", "x_row", "fsaa", "depth", "tile_w", "tile_h", "tls_row", "tls_col", "lst_head", "pad0a", "pad0b"]
-    + ["ctx_flags", "t_min", "org0", "org1", "org2", "p1a", "p1b", "p1c"]
+    + ["ctx_flags", "t_min", "org0", "org1", "org2", "off_bounds", "n_bounds", "p1c"]
     + ["cam_t_max"] + [f"dir{i}" for i in range(3)] + [f"hor{i}" for i in range(3)] + [f"ver{i}" for i in range(3)]
     + [f"hor_a{i}" for i in range(4)] + [f"ver_a{i}" for i in range(4)] + [f"amb{i}" for i in range(3)]
     + ["cam_clamp", "cam_cmask", "pad2"]
