@@ -233,6 +233,15 @@ typedef struct qr_kernel_info
 int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info);
 
 /*
+ * The checked build of the library (make checked: -DQR_CHECKED,
+ * lib/libquadray_b200_checked.so) counts out-of-range element cursors, surface
+ * offsets, tile indices, pixel stores, stack levels and scratch reads that
+ * were not written first, instead of faulting; this returns the counters since
+ * the last call and clears them.  QR_E_STATE in the normal build.
+ */
+int qr_check_counters(qr_ctx *ctx, uint32_t counters[8]);
+
+/*
  * Measured ceiling of the pipe that bounds render0 on this GPU: separately
  * rounded FP32 multiplies and adds (no FMA contraction, as bit parity with the
  * reference demands), in 1e12 operations per second, best of a few launches

@@ -29,6 +29,7 @@ SYMBOLS = (
     "qr_ray_counts", "qr_last_render_ms", "qr_stream", "qr_launch_count",
     "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_fetch", "qr_render_end",
     "qr_frame_notify_slot", "qr_render_rows_notify", "qr_wait_notify", "qr_host_register", "qr_host_unregister",
+    "qr_check_counters",
 )
 
 
@@ -72,6 +73,8 @@ def load_library():
     lib.qr_render_device.restype = ci
     lib.qr_render_rows.argtypes = [vp, vp, ci, ci, ci]
     lib.qr_render_rows.restype = ci
+    lib.qr_check_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    lib.qr_check_counters.restype = ci
     lib.qr_host_register.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     lib.qr_host_register.restype = ci
     lib.qr_host_unregister.argtypes = [vp, vp]
@@ -225,6 +228,12 @@ class Context(object):
         full-frame geometry (possibly another GPU's, see frame_ipc_open)."""
         self._check(self.lib.qr_render_rows(self.h, ctypes.c_void_p(dev_ptr), int(stride),
                                             int(tile_row0), int(tile_row_step)))
+
+    def check_counters(self):
+        """Violation counters of the checked build (raises in the normal build)."""
+        c = (ctypes.c_uint32 * 8)()
+        self._check(self.lib.qr_check_counters(self.h, c))
+        return [int(x) for x in c]
 
     def host_register(self, host_ptr, nbytes):
         """Page-lock a host buffer (e.g. a shared-memory frame) for this context's

@@ -278,6 +278,7 @@ qr_render_kernel(const qr_launch p)
             {
                 const int xq = x0;
                 uint32_t *dst = p.frame + (size_t)(y0 + lane) * p.stride + xq;
+                QR_CHECK(y0 + lane < y_res && xq < x_res && p.stride >= x_res, 4);
                 /* one 128-bit store when the ADDRESS allows it (a caller's frame
                  * or stride need not be 16-byte aligned) */
                 if (xq + 3 < x_res && (((size_t)dst & 15) == 0))
@@ -1015,6 +1016,23 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     {
         QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
     }
+#if defined(QR_CHECKED)
+    {
+        const qr_blob_header *kh = (const qr_blob_header *)ctx->dev[0].blob_h[ctx->slot];
+        qr_check_limits_t lim;
+        lim.elems_lo = (unsigned long long)(p.blob + kh->off_elem);
+        lim.elems_hi = lim.elems_lo + (unsigned long long)kh->n_elem * sizeof(qr_kelem);
+        if (kh->pad0[0] != 0)
+        {
+            /* device-built tile lists: behind the uploaded image */
+            lim.elems_hi = (unsigned long long)p.blob + (uint32_t)kh->pad0[0]
+                         + (unsigned long long)kh->n_tiles * (uint32_t)kh->pad0[1] * sizeof(qr_kelem);
+        }
+        lim.surf_bytes = (uint32_t)kh->n_surf * QR_KSURF_QUADS * 16u;
+        lim.n_tiles = (uint32_t)kh->n_tiles;
+        QR_CUDA(ctx, cudaMemcpyToSymbolAsync(qr_check_limits, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, d.stream));
+    }
+#endif
     void *args[] = { (void *)&p };
     QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
                                   dim3(grid), dim3(threads), args,
@@ -1377,6 +1395,43 @@ extern "C" int qr_wait_notify(qr_ctx *ctx, uint32_t *notify_dev, uint32_t target
     qr_wait_kernel<<<1, 1, 0, d0.stream>>>((unsigned int *)notify_dev, (unsigned int)target);
     QR_CUDA(ctx, cudaGetLastError());
     return QR_OK;
+}
+
+#if defined(QR_CHECKED)
+/* QR_B200_CHECK_SELFTEST=1: every counter is made to fire once (plumbing test) */
+__global__ void qr_check_selftest_kernel()
+{
+    for (int k = 0; k < 7; k++) QR_CHECK(threadIdx.x > 0, k);
+}
+#endif
+
+extern "C" int qr_check_counters(qr_ctx *ctx, uint32_t counters[8])
+{
+    if (ctx == NULL || counters == NULL)
+    {
+        return QR_E_ARG;
+    }
+#if defined(QR_CHECKED)
+    if (getenv("QR_B200_CHECK_SELFTEST") != NULL)
+    {
+        QR_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+        qr_check_selftest_kernel<<<1, 1, 0, ctx->dev[0].stream>>>();
+        QR_CUDA(ctx, cudaGetLastError());
+    }
+    unsigned int c[QR_CHECK_COUNTERS];
+    const unsigned int zero[QR_CHECK_COUNTERS] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        QR_CUDA(ctx, cudaSetDevice(ctx->dev[i].id));
+        QR_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+        QR_CUDA(ctx, cudaMemcpyFromSymbol(c, qr_check_count, sizeof(c)));
+        QR_CUDA(ctx, cudaMemcpyToSymbol(qr_check_count, zero, sizeof(zero)));
+        for (int k = 0; k < 8; k++) counters[k] = (i == 0 ? 0u : counters[k]) + c[k];
+    }
+    return QR_OK;
+#else
+    return qr_fail(ctx, QR_E_STATE, "qr_check_counters: this is not the checked build (make checked)");
+#endif
 }
 
 extern "C" int qr_host_register(qr_ctx *ctx, void *host, size_t bytes, uint32_t **dev_ptr)

@@ -53,6 +53,37 @@
 #define QR_HD_COLD static
 #endif
 
+/* ---- checked build --------------------------------------------------------- */
+/*
+ * -DQR_CHECKED (make checked -> lib/libquadray_b200_checked.so): the kernel
+ * checks its own accesses and counts violations instead of faulting -- what
+ * stands in for compute-sanitizer, which the GPU pool does not allow
+ * (profiles/r02d_compute_sanitizer.txt).  tests/test_gpu_checked_build.py runs
+ * fixtures through it and expects all counters at zero.
+ *   0 element cursor outside the image's element array (incl. device-built tile lists)
+ *   1 surface record offset outside the surface table
+ *   2 best-hit record read without having been written by the walk that reported a hit
+ *   3 continuation stack deeper than the scene's depth
+ *   4 pixel store outside the frame
+ *   5 tile index outside the tile table
+ *   6 shading state read back from the scratch that was not parked by this thread
+ */
+#define QR_CHECK_COUNTERS 8
+#if defined(QR_CHECKED) && defined(__CUDACC__)
+/* (single translation unit: defined here) */
+struct qr_check_limits_t { unsigned long long elems_lo, elems_hi; uint32_t surf_bytes, n_tiles; };
+static __constant__ qr_check_limits_t qr_check_limits;
+static __device__ unsigned int qr_check_count[QR_CHECK_COUNTERS];
+#endif
+#if defined(QR_CHECKED) && defined(__CUDA_ARCH__)
+#define QR_CHECK(cond, code) do { if (!(cond)) atomicAdd(&qr_check_count[code], 1u); } while (0)
+#define QR_CHECKED_ONLY(x) x
+#else
+#define QR_CHECK(cond, code) ((void)0)
+#define QR_CHECKED_ONLY(x)
+#endif
+#define QR_POISON 0x7FC0DEADu   /* a NaN no computation here produces */
+
 /* ---- rounded arithmetic ---------------------------------------------------- */
 
 #if defined(__CUDA_ARCH__)
@@ -254,7 +285,12 @@ struct qr_view
 };
 
 /* quad "q" of the surface record at byte offset "so" (= surface index * 128) */
+#if defined(QR_CHECKED) && defined(__CUDA_ARCH__)
+#define QR_SURF(v, so, q)  (((uint32_t)(so) < qr_check_limits.surf_bytes ? (void)0 : (void)atomicAdd(&qr_check_count[1], 1u)), \
+                            qr_hot<SH>::ld((v).surf, ((uint32_t)(so) < qr_check_limits.surf_bytes ? (uint32_t)(so) : 0u) + (q) * 16u))
+#else
 #define QR_SURF(v, so, q)  qr_hot<SH>::ld((v).surf,  (uint32_t)(so) + (q) * 16u)
+#endif
 /* shading record of the same surface (32 B each) */
 #define QR_SHADE(v, so, q) qr_hot<SH>::ld((v).shade, ((uint32_t)(so) >> 2) + (q) * 16u)
 #define QR_MAT(v, i, q)    qr_hot<SH>::ld((v).mat,   (uint32_t)(i) * (QR_KMAT_QUADS * 16u) + (q) * 16u)
@@ -616,6 +652,17 @@ QR_HD qr_ecur qr_e_at(const qr_kelem *base, uint32_t idx)
 QR_HD qr_kelem qr_e_ld(const qr_ecur c)
 {
     qr_kelem e;
+#if defined(QR_CHECKED) && defined(__CUDA_ARCH__)
+    if (c.p < qr_check_limits.elems_lo || c.p + sizeof(qr_kelem) > qr_check_limits.elems_hi || (c.p & 7) != 0)
+    {
+        atomicAdd(&qr_check_count[0], 1u);
+        e.w = QR_KEND; e.aux = 0;
+        return e;
+    }
+    /* (device-built tile lists are written by the launch before: no .nc) */
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(e.w), "=r"(e.aux) : "l"(c.p));
+    return e;
+#endif
     asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(e.w), "=r"(e.aux) : "l"(c.p));
     return e;
 }
@@ -721,6 +768,7 @@ QR_WALK_FN float qr_walk(const typename qr_hot<SH>::base_t surf, const qr_kelem 
     /* a root t <= 0 (or NaN) can never pass t_min < t when t_min >= 0 */
     const bool no_neg = !(t_min < 0.0f);
     float t_buf = t_max;
+    QR_CHECKED_ONLY(if (mode == QR_MODE_CLOSEST) qr_sc_st1(sc, QR_SC_BEST, 0, QR_POISON);)
 
     qr_ecur cur = qr_e_at(v.elems, head);
     qr_kelem e = qr_e_ld(cur);
@@ -1151,6 +1199,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
         t_max = h.cam_t_max;
         int tx = px / h.tile_w;
         if (tx >= h.tls_row) tx = h.tls_row - 1;
+        QR_CHECK((uint32_t)((py / h.tile_h) * h.tls_row + tx) < (uint32_t)h.n_tiles, 5);
         head = (uint32_t)v.tiles[(py / h.tile_h) * h.tls_row + tx];
         mode = QR_MODE_CLOSEST;
         p_obj = QR_SO_NIL;
@@ -1179,6 +1228,8 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 const qr_f4 a = qr_sc_ld(sc, QR_SC_COL), b = qr_sc_ld(sc, QR_SC_RAY);
                 const qr_f4 c = qr_sc_ld(sc, QR_SC_NRM), d = qr_sc_ld(sc, QR_SC_LOC);
                 const qr_f4 e = qr_sc_ld(sc, QR_SC_TEX);
+                QR_CHECK(qr_f2u(e.w) == (QR_POISON ^ 1u), 6);
+                QR_CHECKED_ONLY(qr_sc_st1(sc, QR_SC_TEX, 3, 0u);)
                 cr = a.x; cg = a.y; cb = a.z; dot = a.w;
                 lrx = b.x; lry = b.y; lrz = b.z; li = qr_f2u(b.w);
                 nx = c.x; ny = c.y; nz = c.z;
@@ -1289,6 +1340,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
             {
                 /* ---------------- SHADE ---------------- */
                 const qr_f4 hr = qr_sc_ld(sc, QR_SC_BEST);
+                QR_CHECK(qr_f2u(hr.x) != QR_POISON, 2);
                 cur_so = qr_f2u(hr.x) & ~127u;
                 const qr_f4 q1 = QR_SURF(v, cur_so, 1), q2 = QR_SURF(v, cur_so, 2);
                 const uint32_t d = qr_f2u(QR_SURF(v, cur_so, 0).w);
@@ -1441,7 +1493,11 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                     qr_sc_st(sc, QR_SC_RAY, lrx, lry, lrz, qr_u2f(li));
                     qr_sc_st(sc, QR_SC_NRM, nx, ny, nz, 0.0f);
                     qr_sc_st(sc, QR_SC_LOC, lcx, lcy, lcz, 0.0f);
+#if defined(QR_CHECKED) && defined(__CUDA_ARCH__)
+                    qr_sc_st(sc, QR_SC_TEX, tr, tg, tb, qr_u2f(QR_POISON ^ 1u));    /* "parked" */
+#else
                     qr_sc_st(sc, QR_SC_TEX, tr, tg, tb, 0.0f);
+#endif
                     rx = x1; ry = x2; rz = x3;
                     t_min = 0.0f;
                     t_max = l0.w;
@@ -1654,6 +1710,7 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
 
             if (push)
             {
+                QR_CHECK(lvl >= 0 && lvl <= QR_STACK_DEPTH && lvl <= h.depth, 3);
                 qr_frame &f = stack[lvl];
                 f.col[0] = cr; f.col[1] = cg; f.col[2] = cb;
                 f.ray[0] = lrx; f.ray[1] = lry; f.ray[2] = lrz;
