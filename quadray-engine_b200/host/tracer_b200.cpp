@@ -215,6 +215,23 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     const uint8_t *blob = g_flat.build(s_inf, &bytes);
     const double t1 = timing ? qr_now_ms() : 0.0;
 
+    {
+        /* QR_B200_DUMP_BLOB=path: the scene blob of the first frame goes to a
+         * file (tools/config5.py times big scenes through the C ABI with it) */
+        static const char *dump = getenv("QR_B200_DUMP_BLOB");
+        static bool dumped = false;
+        if (dump != RT_NULL && !dumped)
+        {
+            dumped = true;
+            FILE *f = fopen(dump, "wb");
+            if (f != RT_NULL)
+            {
+                fwrite(blob, 1, bytes, f);
+                fclose(f);
+            }
+        }
+    }
+
     if (qr_scene_upload(g_ctx, blob, bytes) != QR_OK)
     {
         qr_throw("B200 scene upload failed", g_ctx);

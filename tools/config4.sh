@@ -7,5 +7,7 @@ echo "reference ${N} threads: $(oracle/_ref/qr_ref_harness $A | python -c 'impor
 for d in 0 0,1 0,1,2,3 0,1,2,3,4,5,6,7; do
   s=$(QR_B200_DEVICES=$d build/qr_b200_harness $A | python -c 'import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(j["ms_med"])')
   p=$(QR_B200_DEVICES=$d QR_B200_PIPELINE=1 build/qr_b200_harness $A | python -c 'import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(j["ms_med"])')
-  echo "GPUs $d: synchronous $s ms, pipelined $p ms"
+  # engine tiling off, tile lists built on the device
+  t=$(QR_B200_DEVICES=$d QR_B200_PIPELINE=1 QR_B200_EXPECT_DEVICE_TILING=1 build/qr_b200_harness $A -p 0x0230FFB9 | python -c 'import json,sys; j=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(j["ms_med"])')
+  echo "GPUs $d: synchronous $s ms, pipelined $p ms, pipelined + device-side tiling $t ms"
 done

@@ -124,6 +124,8 @@ CASES_CRC = {
     "synth10k_1080p_a4c": "-s synth -N 10000 -x 1920 -y 1080 -a 2",
     "synth10k_8k_a4c":    "-s synth -N 10000 -x 7680 -y 4320 -a 2",
     "synth100k_1080p_c":  "-s synth -N 100000 -x 1920 -y 1080",
+    # config 5 at the stated size: 100 k quadrics, 7680 x 4320, 4xAA
+    "synth100k_8k_a4c":   "-s synth -N 100000 -x 7680 -y 4320 -a 2",
 }
 
 
