@@ -412,6 +412,21 @@ def main_gpu(args, rank, world, local_rank):
     rays_measured = float(rays_t.item()) / args.steps
     rays = meta["rays"]["total"]
 
+    if os.environ.get("QR_BENCH_DIAG"):
+        # diagnostics (stderr): this rank's kernel-only time of its share, frame by frame,
+        # with the ranks in lockstep (barrier per frame) and with the L2 flush as in the timed loop
+        ks = []
+        for _ in range(10):
+            flush.fill_(rank + 1)
+            barrier()
+            qstream.wait_stream(cur)
+            render_shard()
+            ctx.sync()
+            ks.append(ctx.last_render_ms())
+            barrier()
+        sys.stderr.write("diag rank %d: share kernel ms min %.3f med %.3f max %.3f; timed loop mean %.3f ms/step\n"
+                         % (rank, min(ks), sorted(ks)[len(ks) // 2], max(ks), dev_ms / args.steps))
+
     # parity of what was just timed (rank 0 holds the assembled frame)
     parity = None
     if rank == 0:

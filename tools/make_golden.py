@@ -126,6 +126,11 @@ CASES_CRC = {
     "synth100k_1080p_c":  "-s synth -N 100000 -x 1920 -y 1080",
     # config 5 at the stated size: 100 k quadrics, 7680 x 4320, 4xAA
     "synth100k_8k_a4c":   "-s synth -N 100000 -x 7680 -y 4320 -a 2",
+    # the same clouds with SHARED GLOBAL lists (RT_OPTS_RENDER / SHADOW* / 2SIDED* off,
+    # engine.cpp:2170-2173, 2483-2486): the engine builds no per-surface lists (its O(n^2)
+    # part), every ray walks the camera list's bounding-volume tree
+    "synth100k_1080p_glc":  "-s synth -N 100000 -x 1920 -y 1080 -p 0x023001BF",
+    "synth10k_8k_a4_glc":   "-s synth -N 10000 -x 7680 -y 4320 -a 2 -p 0x023001BF",
 }
 
 
