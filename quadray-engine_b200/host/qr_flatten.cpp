@@ -394,14 +394,6 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     rt_ELEM **tl = (rt_ELEM **)s_inf->tiles;
     int32_t n_tiles = h.tls_row * h.tls_col;
     tiles.resize(n_tiles);
-    for (int32_t t = 0; t < n_tiles; t++)
-    {
-        if (t + 8 < n_tiles && tl[t + 8] != RT_NULL)
-        {
-            QR_PREFETCH(tl[t + 8]);
-        }
-        tiles[t] = list_head(tl[t], LIST_SURF);
-    }
 
     /* RT_OPTS_TILING off: every tile head is the camera list
      * (engine.cpp:3236-3248).  The bounding boxes the engine's stile() would
@@ -410,6 +402,26 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     for (int32_t t = 1; t < n_tiles && untiled; t++)
     {
         untiled = tl[t] == tl[0];
+    }
+    if (untiled)
+    {
+        /* one list, named once */
+        const int32_t head = list_head(tl[0], LIST_SURF);
+        for (int32_t t = 0; t < n_tiles; t++)
+        {
+            tiles[t] = head;
+        }
+    }
+    else
+    {
+        for (int32_t t = 0; t < n_tiles; t++)
+        {
+            if (t + 8 < n_tiles && tl[t + 8] != RT_NULL)
+            {
+                QR_PREFETCH(tl[t + 8]);
+            }
+            tiles[t] = list_head(tl[t], LIST_SURF);
+        }
     }
     std::vector<std::pair<int32_t, const rt_BOUND *> > clist_bounds;
     if (untiled)
