@@ -212,10 +212,7 @@ template <> struct qr_hot<true>
 #define QR_SC_MISC   5
 #define QR_SC_WORG   6      /* world origin / direction of the ray being walked: parked for */
 #define QR_SC_WRAY   7      /* the walk, which transforms its copy in place inside nodes */
-#define QR_SC_NORG   8      /* the ray in the space of the node being opened: written and read */
-#define QR_SC_NRAY   9      /* straight back, so that the walk's ray registers are (re)defined by
-                               loads only and no copies of them are carried around the loop */
-#define QR_SC_QUADS  10
+#define QR_SC_QUADS  8
 
 #if defined(__CUDACC__)
 /* (the host pass of nvcc parses these too; it never calls them) */
@@ -865,9 +862,7 @@ QR_WALK_FN float qr_walk(const typename qr_hot<SH>::base_t surf, const qr_kelem 
                         }
                         float n0, n1, n2;
                         qr_xform(q5t, q6, tckz, trm, cr0, cr1, cr2, n0, n1, n2);
-                        qr_sc_st(sc, QR_SC_NRAY, n0, n1, n2, 0.0f);
-                        const qr_f4 nr = qr_sc_ld(sc, QR_SC_NRAY);
-                        cr0 = nr.x; cr1 = nr.y; cr2 = nr.z;
+                        cr0 = n0; cr1 = n1; cr2 = n2;
                     }
                     else
                     {
@@ -1045,12 +1040,9 @@ QR_WALK_FN float qr_walk(const typename qr_hot<SH>::base_t surf, const qr_kelem 
             float n0, n1, n2;
             qr_xform(q5, q6, tckz, trm, qr_sub(bo0, q0.x), qr_sub(bo1, q0.y), qr_sub(bo2, q0.z),
                      n0, n1, n2);
-            qr_sc_st(sc, QR_SC_NORG, n0, n1, n2, 0.0f);
+            bo0 = n0; bo1 = n1; bo2 = n2;
             qr_xform(q5, q6, tckz, trm, cr0, cr1, cr2, n0, n1, n2);
-            qr_sc_st(sc, QR_SC_NRAY, n0, n1, n2, 0.0f);
-            const qr_f4 no = qr_sc_ld(sc, QR_SC_NORG), nr = qr_sc_ld(sc, QR_SC_NRAY);
-            bo0 = no.x; bo1 = no.y; bo2 = no.z;
-            cr0 = nr.x; cr1 = nr.y; cr2 = nr.z;
+            cr0 = n0; cr1 = n1; cr2 = n2;
         }
         else
         if (kind == QR_K_CLOSE)
