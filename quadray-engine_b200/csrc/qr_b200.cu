@@ -47,8 +47,8 @@ static const qr_shape g_shapes[] = { {256, 2}, {512, 1}, {640, 1}, {768, 1}, {38
                                      {896, 1}, {1024, 1} };
 #define QR_N_SHAPES     8
 #define QR_DEFAULT_SHAPE 2
-#define QR_BIG_SHAPE     3          /* 768 threads at 80 registers: 24 warps per SM and few spills
-                                       (1024 x 64 spills p_obj into the walk, 640 x 96 has 20 warps) */
+#define QR_BIG_SHAPE     6          /* 896 threads at 72 registers: 28 warps per SM (1080p 4xAA demo scene:
+                                       1.46 ms; 1.53 at 768 x 80, 1.48 at 1024 x 64, 1.6 at 640 x 96) */
 #define QR_BIG_FRAME_ITEMS 60000    /* work items (32 samples each) per GPU from which QR_BIG_SHAPE pays */
 
 /* ------------------------------------------------------------------ PTX --- */

@@ -314,15 +314,20 @@ QR_HD void qr_view_init(qr_view<false> &v, const void *img)
 /* continuation of a level that waits for a child ray */
 struct qr_frame
 {
+    /* a level that waits for its REFLECTION child (the last thing it does)
+     * needs only the first five words back: colour so far and C_RFL.  Writing
+     * and reading the whole frame made thread-local memory the main user of
+     * L1 (the list elements share it): L1 hit rate 72 % -> 95 % */
     float    col[3];         /* COL of the level so far */
+    float    c_rfl;          /* ctx_C_RFL */
+    int32_t  stage;          /* 0: child is the refraction ray, 1: reflection */
+    float    c_trn;          /* ctx_C_TRN */
+    uint32_t so;             /* surface being shaded */
+    int32_t  flg;            /* ctx_LOCAL(FLG): side | props */
     float    ray[3];         /* RAY_X/Y/Z of the level */
     float    hit[3];         /* HIT_X/Y/Z */
     float    nrm[3];         /* NRM_X/Y/Z */
     float    loc[3];         /* NRM_I/J/K: stored local hit (tracer.cpp:2272-2282) */
-    float    c_trn, c_rfl;   /* ctx_C_TRN / ctx_C_RFL */
-    uint32_t so;             /* surface being shaded */
-    int32_t  flg;            /* ctx_LOCAL(FLG): side | props */
-    int32_t  stage;          /* 0: child is the refraction ray, 1: reflection */
 };
 
 #define QR_MODE_CLOSEST 0
@@ -1517,6 +1522,16 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 lvl--;
                 const qr_frame &f = stack[lvl];
                 const float ccr = cr, ccg = cg, ccb = cb;
+                if (f.stage != 0)
+                {
+                    /* RF_ret 3868-3884 and RF_mix 3888-3908: the level is
+                     * finished with this; nothing else of it is needed */
+                    const float rfl = f.c_rfl;
+                    cr = qr_add(qr_mul(ccr, rfl), f.col[0]);
+                    cg = qr_add(qr_mul(ccg, rfl), f.col[1]);
+                    cb = qr_add(qr_mul(ccb, rfl), f.col[2]);
+                    continue;
+                }
                 cr = f.col[0]; cg = f.col[1]; cb = f.col[2];
                 lrx = f.ray[0]; lry = f.ray[1]; lrz = f.ray[2];
                 ox = f.hit[0]; oy = f.hit[1]; oz = f.hit[2];
@@ -1524,18 +1539,9 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 lcx = f.loc[0]; lcy = f.loc[1]; lcz = f.loc[2];
                 c_trn = f.c_trn; c_rfl = f.c_rfl;
                 cur_so = f.so; l_flg = f.flg;
-                if (f.stage == 0)
-                {
-                    /* TR_ret 3534-3552 */
-                    xr = qr_mul(ccr, c_trn); xg = qr_mul(ccg, c_trn); xb = qr_mul(ccb, c_trn);
-                    resume = 1;
-                }
-                else
-                {
-                    /* RF_ret 3868-3884 */
-                    xr = qr_mul(ccr, c_rfl); xg = qr_mul(ccg, c_rfl); xb = qr_mul(ccb, c_rfl);
-                    resume = 2;
-                }
+                /* TR_ret 3534-3552 */
+                xr = qr_mul(ccr, c_trn); xg = qr_mul(ccg, c_trn); xb = qr_mul(ccb, c_trn);
+                resume = 1;
             }
 
             const int side = l_flg & 1;
@@ -1705,12 +1711,18 @@ QR_HD void qr_trace_sample(const qr_view<SH> &v, int px, int py, int lane4,
                 QR_CHECK(lvl >= 0 && lvl <= QR_STACK_DEPTH && lvl <= h.depth, 3);
                 qr_frame &f = stack[lvl];
                 f.col[0] = cr; f.col[1] = cg; f.col[2] = cb;
-                f.ray[0] = lrx; f.ray[1] = lry; f.ray[2] = lrz;
-                f.hit[0] = ox; f.hit[1] = oy; f.hit[2] = oz;
-                f.nrm[0] = nx; f.nrm[1] = ny; f.nrm[2] = nz;
-                f.loc[0] = lcx; f.loc[1] = lcy; f.loc[2] = lcz;
-                f.c_trn = c_trn; f.c_rfl = c_rfl;
-                f.so = cur_so; f.flg = l_flg; f.stage = push_stage;
+                f.c_rfl = c_rfl; f.stage = push_stage;
+                if (push_stage == 0)
+                {
+                    /* a level that waits for its refraction child goes on
+                     * afterwards (TR_mix, reflection): all of it */
+                    f.ray[0] = lrx; f.ray[1] = lry; f.ray[2] = lrz;
+                    f.hit[0] = ox; f.hit[1] = oy; f.hit[2] = oz;
+                    f.nrm[0] = nx; f.nrm[1] = ny; f.nrm[2] = nz;
+                    f.loc[0] = lcx; f.loc[1] = lcy; f.loc[2] = lcz;
+                    f.c_trn = c_trn;
+                    f.so = cur_so; f.flg = l_flg;
+                }
                 /* the child's walk finds this level's local hit in the scratch */
                 qr_sc_st(sc, QR_SC_LOC, lcx, lcy, lcz, 0.0f);
                 rx = nwx; ry = nwy; rz = nwz;
