@@ -3,7 +3,7 @@
 # scene staging, 128-bit stores, system-scope atomics of the completion counter, no tensor ops.
 # usage: tools/sass_evidence.sh > profiles/rNN_sass_evidence.txt
 LIB=quadray-engine_b200/lib/libquadray_b200.so
-K='_Z16qr_render_kernelILb1ELi768ELi1EEv9qr_launch'
+K='_Z16qr_render_kernelILb1ELi896ELi1EEv9qr_launch'
 T=$(mktemp -d); (cd $T && cuobjdump -xelf all $OLDPWD/$LIB > /dev/null); C=$(ls $T/*.cubin | head -1)
 echo "library: $LIB ($(git rev-parse --short HEAD 2>/dev/null))"; echo "kernel : $K"
 nvdisasm -c $C > $T/all.sass
