@@ -518,47 +518,38 @@ def main_gpu(args, rank, world, local_rank):
         # qr_render_rows(shared host frame) + wait for the PREVIOUS frame's
         # kernel + a flag in the shared segment; rank 0 sees the previous frame
         # complete when every rank's flag has reached it, and reads it.
-        import mmap
         fbytes = h * x_row * 4
-        seg_bytes = 2 * fbytes + 4096
         shm_name = "/dev/shm/qr_b200_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "x"))
+        ring = None
         if rank == 0:
-            fd = os.open(shm_name, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o600)
-            os.ftruncate(fd, seg_bytes)
+            ring = pkg.SharedFrameRing(shm_name, h, x_row, world, rank, create=True)
         dist.barrier()
         if rank != 0:
-            fd = os.open(shm_name, os.O_RDWR)
-        seg = mmap.mmap(fd, seg_bytes)
-        seg_np = np.frombuffer(seg, dtype=np.uint8)
-        seg_dev = ctx.host_register(seg_np.ctypes.data, seg_bytes)
-        frames_h = [seg_np[k * fbytes:(k + 1) * fbytes].view(np.uint32).reshape(h, x_row) for k in range(2)]
-        flags = seg_np[2 * fbytes:2 * fbytes + 8 * (world + 1)].view(np.int64)   # [rank]: rows done, [world]: consumed
-        if rank == 0:
-            flags[:] = 0
+            ring = pkg.SharedFrameRing(shm_name, h, x_row, world, rank, create=False)
+        seg_dev = ctx.host_register(ring.host_ptr, ring.nbytes)
         dist.barrier()
         ctx.pipeline(True)
         evq = [torch.cuda.Event(), torch.cuda.Event()]
         seen = [0]
 
         def run_sharded(n):
-            """n frames; returns after the last one is complete in host memory."""
+            """n frames (numbered from seen + 1); returns after the last one is
+            complete in host memory."""
             base = seen[0]
             for i in range(n + 1):
-                k = base + i
+                k = base + i + 1
                 if i < n:
                     ctx.upload(blob_h)
-                    while int(flags[world]) < k - 1:        # the host frame k uses is free (frame k - 2 consumed)
-                        pass
-                    ctx.render_rows(seg_dev + (k & 1) * fbytes, x_row, rank, world)
+                    ring.wait_free(k)                       # frame k - 2 has been consumed
+                    ctx.render_rows(seg_dev + ring.frame_offset(k), x_row, rank, world)
                     evq[k & 1].record(qstream)
                 if i > 0:
                     evq[(k - 1) & 1].synchronize()          # this rank's rows of frame k - 1 are in host memory
-                    flags[rank] = k                         # ... says so to rank 0
+                    ring.mark_done(k - 1)                   # ... says so to rank 0
                     if rank == 0:
-                        while int(flags[:world].min()) < k:
-                            pass
-                        _ = int(frames_h[(k - 1) & 1][h // 2, w // 2])      # the step's result is read on the host
-                        flags[world] = k                    # ... and its buffer handed back
+                        ring.wait_complete(k - 1)
+                        _ = int(ring.frame(k - 1)[h // 2, w // 2])          # the step's result is read on the host
+                        ring.release(k - 1)                 # ... and its buffer handed back
             seen[0] = base + n
 
         run_sharded(3)
@@ -567,22 +558,18 @@ def main_gpu(args, rank, world, local_rank):
         run_sharded(args.steps)
         e2e_s = time.perf_counter() - t0
         barrier()
-        e2e_parity = int((frames_h[(seen[0] - 1) & 1][:, :w] != ref_frame).sum()) if rank == 0 else None
+        e2e_parity = int((ring.frame(seen[0])[:, :w] != ref_frame).sum()) if rank == 0 else None
         ctx.pipeline(False)
         ctx.upload(blob_h)
         ctx.sync()
-        ctx.host_unregister(seg_np.ctypes.data)
+        ctx.host_unregister(ring.host_ptr)
         d2h = int(sum(min(tile_h, h - t * tile_h) for t in range(rank, tls_col, world)) * w * 4)
         e2e_path_n = ("per step and rank: qr_scene_upload(host blob: pack + pinned H2D, two scene slots) + "
                       "qr_render_rows(its tile rows, stored by the kernel straight into ONE page-locked host frame "
                       "shared by all ranks, over each GPU's own PCIe link) + wait for the previous frame; "
                       "two frames in flight; rank 0 reads the frame when every rank has flagged it")
         dist.barrier()
-        if rank == 0:
-            try:
-                os.unlink(shm_name)
-            except OSError:
-                pass
+        ring.close(unlink=(rank == 0))
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     bytes_t = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -332,3 +332,77 @@ def tile_row_span(y_res, tile_h, tile_row):
     """Frame rows [y0, y1) of one tile row."""
     y0 = tile_row * tile_h
     return y0, min(y0 + tile_h, y_res)
+
+
+class SharedFrameRing(object):
+    """Two host frames shared by the ranks of one box (one process per GPU), in
+    ONE POSIX shared-memory segment -- the role RooT's XShm image plays for the
+    reference's worker threads.  Every rank page-locks its mapping
+    (Context.host_register) and renders its tile rows straight into frame
+    k & 1; the segment also carries the hand-shake:
+
+        flags[rank]  last frame whose rows this rank has completed
+        flags[world] last frame rank 0 has consumed (its buffer is free again)
+
+    Frames are numbered from 1.  Protocol per frame k on every rank:
+        wait_free(k); render rows into frame(k); ... ; mark_done(k)
+    and on rank 0:  wait_complete(k); read frame(k); release(k).
+    Host-side logic only (no CUDA here): tests/test_sharding_gloo.py runs it on
+    the CPU with the oracle standing in for the device."""
+
+    def __init__(self, path, y_res, x_row, world, rank, create):
+        import mmap
+        self.path, self.world, self.rank = path, int(world), int(rank)
+        self.fbytes = int(y_res) * int(x_row) * 4
+        self.nbytes = 2 * self.fbytes + 4096
+        flags = os.O_RDWR | ((os.O_CREAT | os.O_TRUNC) if create else 0)
+        fd = os.open(path, flags, 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, self.nbytes)
+            self.map = mmap.mmap(fd, self.nbytes)
+        finally:
+            os.close(fd)
+        self.bytes = np.frombuffer(self.map, dtype=np.uint8)
+        self.frames = [self.bytes[k * self.fbytes:(k + 1) * self.fbytes].view(np.uint32).reshape(int(y_res), int(x_row))
+                       for k in range(2)]
+        self.flags = self.bytes[2 * self.fbytes:2 * self.fbytes + 8 * (self.world + 1)].view(np.int64)
+        if create:
+            self.flags[:] = 0
+
+    @property
+    def host_ptr(self):
+        return self.bytes.ctypes.data
+
+    def frame(self, k):
+        return self.frames[k & 1]
+
+    def frame_offset(self, k):
+        return (k & 1) * self.fbytes
+
+    def wait_free(self, k):
+        """Frame k's buffer is free once frame k - 2 has been consumed."""
+        while int(self.flags[self.world]) < k - 2:
+            pass
+
+    def mark_done(self, k):
+        self.flags[self.rank] = k
+
+    def wait_complete(self, k):
+        while int(self.flags[:self.world].min()) < k:
+            pass
+
+    def release(self, k):
+        self.flags[self.world] = k
+
+    def close(self, unlink=False):
+        self.frames, self.flags, self.bytes = None, None, None
+        try:
+            self.map.close()
+        except BufferError:
+            pass
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

@@ -67,3 +67,63 @@ def test_two_ranks_gather_equals_single(tmp_path, entry):
     got = np.load(out)
     _, ref, _ = entry.load_golden("test05_odd")
     assert np.array_equal(got, ref)
+
+
+def _ring_worker(rank, world, port, shm_path, out_path):
+    """The end-to-end protocol of bench.py at N > 1 on the CPU: every rank
+    "renders" (oracle) its tile rows of frame k straight into the shared host
+    frame k & 1, flags it, rank 0 consumes complete frames and hands the
+    buffers back; two frames in flight, several frames of different scenes."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = ge.load_package()
+    names = ["test05_odd", "test05_odd_nt", "test05_odd"]       # same geometry, two scene blobs
+    blobs = [ge.load_golden(n) for n in names]
+    h, w = blobs[0][1].shape
+    ring = None
+    if rank == 0:
+        ring = pkg.SharedFrameRing(shm_path, h, w, world, rank, create=True)
+    dist.barrier()
+    if rank != 0:
+        ring = pkg.SharedFrameRing(shm_path, h, w, world, rank, create=False)
+    dist.barrier()
+    got = []
+    n = 5
+    for i in range(n + 1):
+        k = i + 1
+        if i < n:
+            blob = blobs[i % len(blobs)][0]
+            ring.wait_free(k)
+            if rank == 0 and k > 2:
+                assert int(ring.flags[world]) >= k - 2
+            for tr in pkg.rank_tile_rows(h, 8, rank, world):
+                y0, y1 = pkg.tile_row_span(h, 8, tr)
+                part, _, _ = ge.oracle_render(blob, packet=1, y0=y0, y1=y1)
+                ring.frame(k)[y0:y1, :w] = part[y0:y1]
+        if i > 0:
+            ring.mark_done(k - 1)
+            if rank == 0:
+                ring.wait_complete(k - 1)
+                got.append(ring.frame(k - 1).copy())
+                ring.release(k - 1)
+    if rank == 0:
+        np.save(out_path, np.stack(got))
+    dist.barrier()
+    ring.close(unlink=(rank == 0))
+    dist.destroy_process_group()
+
+
+def test_shared_frame_ring_two_ranks(tmp_path, entry):
+    out = str(tmp_path / "frames.npy")
+    shm = "/dev/shm/qr_b200_test_%d" % os.getpid()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_ring_worker, args=(2, port, shm, out), nprocs=2, join=True)
+    got = np.load(out)
+    assert got.shape[0] == 5
+    refs = [entry.load_golden(n)[1] for n in ("test05_odd", "test05_odd_nt", "test05_odd")]
+    for i in range(5):
+        assert np.array_equal(got[i], refs[i % 3]), i
+    assert not os.path.exists(shm)
