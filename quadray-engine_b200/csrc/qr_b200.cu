@@ -114,6 +114,18 @@ struct qr_launch
 
 extern __shared__ __align__(128) uint8_t qr_smem[];
 
+#if defined(QR_ITEMLOG)
+/* tuning build only (make itemlog): start, duration and SM of every work item */
+struct qr_itemlog_t { unsigned long long t0; unsigned int dt, sm; };
+static __device__ qr_itemlog_t *qr_itemlog_ptr;
+__device__ __forceinline__ unsigned long long qr_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 /*
  * STAGED = true: the kscene prefix (header, surfaces, shading records,
  * materials, lights) is copied to shared memory by TMA and every access to it
@@ -212,7 +224,10 @@ qr_render_kernel(const qr_launch p)
 
     while (item < n_items)
     {
-
+#if defined(QR_ITEMLOG)
+        const unsigned long long il_t0 = qr_globaltimer();
+        const unsigned int il_item = item;
+#endif
         const unsigned int tile = item / per_tile;
         const unsigned int sub  = item % per_tile;
         const int brow = (int)(sub / (unsigned int)pk_per_row);
@@ -294,6 +309,15 @@ qr_render_kernel(const qr_launch p)
                 }
             }
         }
+#if defined(QR_ITEMLOG)
+        if (lane == 0 && qr_itemlog_ptr != NULL)
+        {
+            unsigned int sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            qr_itemlog_t rec = { il_t0, (unsigned int)(qr_globaltimer() - il_t0), sm };
+            qr_itemlog_ptr[il_item] = rec;
+        }
+#endif
         /* drawn when it is needed, not one item ahead: an item reserved early
          * waits behind the one in progress while other warps run dry, which
          * doubles the tail of a launch; the atomic's latency is hidden by the
@@ -1033,12 +1057,38 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
         QR_CUDA(ctx, cudaMemcpyToSymbolAsync(qr_check_limits, &lim, sizeof(lim), 0, cudaMemcpyHostToDevice, d.stream));
     }
 #endif
+#if defined(QR_ITEMLOG)
+    qr_itemlog_t *il_dev = NULL;
+    if (getenv("QR_B200_ITEM_LOG") != NULL)
+    {
+        QR_CUDA(ctx, cudaMalloc((void **)&il_dev, (size_t)n_items * sizeof(qr_itemlog_t)));
+        QR_CUDA(ctx, cudaMemsetAsync(il_dev, 0, (size_t)n_items * sizeof(qr_itemlog_t), d.stream));
+    }
+    QR_CUDA(ctx, cudaMemcpyToSymbolAsync(qr_itemlog_ptr, &il_dev, sizeof(il_dev), 0, cudaMemcpyHostToDevice, d.stream));
+#endif
     void *args[] = { (void *)&p };
     QR_CUDA(ctx, cudaLaunchKernel((const void *)qr_kernel_of(ctx->stage_bytes != 0, ctx->shape),
                                   dim3(grid), dim3(threads), args,
                                   ctx->stage_bytes + (size_t)threads * QR_SC_QUADS * 16u, d.stream));
     QR_CUDA(ctx, cudaGetLastError());
     QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+#if defined(QR_ITEMLOG)
+    if (il_dev != NULL)
+    {
+        /* every launch overwrites the file: the last one of a run is kept */
+        qr_itemlog_t *il = (qr_itemlog_t *)malloc((size_t)n_items * sizeof(qr_itemlog_t));
+        QR_CUDA(ctx, cudaMemcpyAsync(il, il_dev, (size_t)n_items * sizeof(qr_itemlog_t), cudaMemcpyDeviceToHost, d.stream));
+        QR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+        FILE *f = fopen(getenv("QR_B200_ITEM_LOG"), "wb");
+        if (f != NULL)
+        {
+            fwrite(il, sizeof(qr_itemlog_t), n_items, f);
+            fclose(f);
+        }
+        free(il);
+        cudaFree(il_dev);
+    }
+#endif
     d.timed = true;
     ctx->launches++;
     {
