@@ -46,6 +46,9 @@ extern "C" {
 #define QR_PROP_DIFFUSE  0x00004000
 #define QR_PROP_SPECULAR 0x00008000
 
+/* qr_blob_header::flags */
+#define QR_BLOB_PT          0x100u
+
 /* context flags, core/tracer/tracer.cpp:504-512 */
 #define QR_FLAG_SIDE_OUTER 0
 #define QR_FLAG_SIDE_INNER 1
@@ -64,7 +67,7 @@ typedef struct qr_blob_header
     uint32_t magic;
     uint32_t version;
     uint32_t total_bytes;
-    uint32_t flags;           /* reserved, 0 */
+    uint32_t flags;           /* QR_BLOB_PT: the engine asked for the path tracer (rt_SIMD_INFOX::pt_on) */
 
     /* rt_SIMD_INFOX externals, tracer.h:154-216 (engine.cpp:842-857) */
     int32_t  x_res;           /* frm_w */
@@ -155,7 +158,9 @@ typedef struct qr_material
     float    c_rfl, c_trn, c_rfr, rfr_2, c_rcp, ext_2;
     float    clamp;           /* 255.0 */
     uint32_t cmask;           /* 255 */
-    int32_t  pad[11];
+    float    col[3];          /* col_r/g/b: self-emission of a light-emitting surface, path tracer
+                                 only (object.cpp:1332-1372); zero in blobs written before it existed */
+    int32_t  pad[8];
 } qr_material;
 
 #define QR_MAT_WORDS 32

@@ -77,6 +77,11 @@ typedef struct R
     lvl_t lv[LEVELS];
     W     mem[LEVELS * STEP + NF][MAXS];
     qr_oracle_stats st;
+    /* path tracer (pt_on): seed / colour planes of the frame, the slot of the
+     * current packet's lane 0 in them (inf_PRNGS), 1 / samples and 1 - that */
+    qr_oracle_pt *pt;
+    size_t prngs;
+    float  pts_o, pts_u;
 } R;
 
 #define FLD(c, f) (r->mem[(c) + (f)])
@@ -94,6 +99,38 @@ static inline float    u2f(uint32_t u) { W w; w.u = u; return w.f; }
 static inline uint32_t f2u(float f)    { W w; w.f = f; return w.u; }
 
 static inline float rsq(float x) { return 1.0f / sqrtf(x); }
+
+/* sinps_rr / cosps_rr, tracer.cpp:1032-1057: power series, the terms added by
+ * fused multiply-adds (fmaps3ld is VFMADD231PS on the AVX-512 targets) */
+static inline float sin_ps(float x)
+{
+    const float t1 = x * x;
+    float xd = x;
+    float xs = xd * t1;
+    xd = fmaf(xs, -0.1666666666666666666666666666666666666666666f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, +0.0083333333333333333333333333333333333333333f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, -0.0001984126984126984126984126984126984126984f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, +0.0000027557319223985890652557319223985890652f, xd);
+    return xd;
+}
+
+static inline float cos_ps(float x)
+{
+    const float t1 = x * x;
+    float xd = 1.0f;
+    float xs = xd * t1;
+    xd = fmaf(xs, -0.5f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, +0.0416666666666666666666666666666666666666666f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, -0.0013888888888888888888888888888888888888888f, xd);
+    xs = xs * t1;
+    xd = fmaf(xs, +0.0000248015873015873015873015873015873015873f, xd);
+    return xd;
+}
 
 /* cvnps: round to nearest even, x86 "integer indefinite" out of range */
 static inline int32_t cvn(float x)
@@ -421,6 +458,25 @@ static void clip(R *r, int lvl, int ei, W *x7)
     }
 }
 
+/*
+ * GET_RANDOM 1014-1028, RT_PRNG = LCG24 (tracer.h:53, engine.cpp:867-873): the
+ * seed of every lane advances s = s * 214013 + 2531011 (mod 2^32) and is stored
+ * for the lanes of TMASK only; the number is bits 8..31 of the new seed over
+ * 2^24.  Lanes outside TMASK get a number too (from a seed that stays).
+ */
+static void get_random(R *r, int c, W *x0)
+{
+    for (int l = 0; l < r->n; l++)
+    {
+        uint32_t sd = r->pt->pseed[r->prngs + (size_t)l];
+        sd = sd * 214013u + 2531011u;
+        if (FLD(c, TMASK)[l].u) r->pt->pseed[r->prngs + (size_t)l] = sd;
+        const float a = (float)(int32_t)((sd >> 8) & 0xFFFFFFu);
+        const float b = (float)(int32_t)0xFFFFFF + 1.0f;
+        x0[l].f = a / b;
+    }
+}
+
 /* ---- material: tracer.cpp:4139-4193, 4280-4336, 4845-4905, 2166-3947 ------ */
 /* kind: 1 PL_mat, 2 QD_mat, 3 TP_mat.  Returns 1 when the walk must stop
  * (OO_out from CHECK_SHAD), 0 to return to the calling solver (SR_rt*). */
@@ -599,6 +655,151 @@ static int material(R *r, int lvl, int ei, int kind)
         FLD(c, F_PRB)[l] = FLD(c, TMASK)[l];
     }
 
+    if (r->pt != NULL)
+    {
+        /* path tracer, 2339-2701: instead of the lights one diffuse bounce */
+        W x1[MAXS], x2[MAXS], x3[MAXS];
+        for (int l = 0; l < n; l++) x1[l].u = x2[l].u = x3[l].u = 0;
+
+        int bounce = (props & QR_PROP_DIFFUSE) != 0;        /* CHECK_PROP(PT_mix, RT_PROP_DIFFUSE) */
+        if (bounce && !(r->depth > QR_STACK_DEPTH - 5))
+        {
+            /* 2352-2396 (RT_FEAT_PT_SPLIT_DEPTH): deeper levels go on with the
+             * probability of the brightest colour channel */
+            W x0[MAXS], x4[MAXS];
+            for (int l = 0; l < n; l++)
+            {
+                float a = FLD(c, TEX + 0)[l].f;             /* maxps: the source when unordered */
+                a = a > FLD(c, TEX + 1)[l].f ? a : FLD(c, TEX + 1)[l].f;
+                a = a > FLD(c, TEX + 2)[l].f ? a : FLD(c, TEX + 2)[l].f;
+                x4[l].f = a;
+            }
+            get_random(r, c, x0);
+            for (int l = 0; l < n; l++)
+            {
+                x0[l].u = m_lt(x0[l].f, x4[l].f) & FLD(c, F_PRB)[l].u;
+                FLD(c, F_PRB)[l] = x0[l];
+                FLD(c, TMASK)[l] = x0[l];
+            }
+            if (none(x0, n))
+            {
+                bounce = 0;                                 /* PT_chk -> PT_mix */
+            }
+            else
+            {
+                for (int l = 0; l < n; l++)
+                {
+                    const float x5 = 1.0f / x4[l].f;        /* rcpps, all lanes */
+                    for (int k = 0; k < 3; k++) FLD(c, TEX + k)[l].f = FLD(c, TEX + k)[l].f * x5;
+                }
+            }
+        }
+        if (bounce)
+        {
+            /* 2398-2530: orthonormal basis around the normal (its fields are
+             * borrowed ones: TEX_U, TEX_V, C_PTR, C_ACC, F_RFL, T_VAL) */
+            W x6[MAXS], x0[MAXS];
+            for (int l = 0; l < n; l++)
+            {
+                const float n1 = FLD(c, NRM + 0)[l].f, n2 = FLD(c, NRM + 1)[l].f, n3 = FLD(c, NRM + 2)[l].f;
+                const float r4 = FLD(c, RAY + 0)[l].f, r5 = FLD(c, RAY + 1)[l].f, r6 = FLD(c, RAY + 2)[l].f;
+                float a0, a7;
+                a0 = n2 * r6; a7 = n3 * r5; float u4 = a0 - a7;
+                a0 = n3 * r4; a7 = n1 * r6; float u5 = a0 - a7;
+                a0 = n1 * r5; a7 = n2 * r4; float u6 = a0 - a7;
+                float s1 = u4 * u4, s2 = u5 * u5, s3 = u6 * u6;
+                s1 = s1 + s2;
+                s1 = s1 + s3;
+                const float inv = rsq(s1);
+                u4 = u4 * inv; u5 = u5 * inv; u6 = u6 * inv;
+                FLD(c, TEX_U)[l].f = u4; FLD(c, TEX_V)[l].f = u5; FLD(c, C_PTR)[l].f = u6;
+                a0 = n2 * u6; a7 = n3 * u5; FLD(c, C_ACC)[l].f = a0 - a7;
+                a0 = n3 * u4; a7 = n1 * u6; FLD(c, F_RFL)[l].f = a0 - a7;
+                a0 = n1 * u5; a7 = n2 * u4; FLD(c, T_VAL)[l].f = a0 - a7;
+            }
+            /* 2532-2590: cosine-weighted direction over the hemisphere */
+            get_random(r, c, x0);
+            for (int l = 0; l < n; l++)
+            {
+                x6[l].f = x0[l].f;
+                float a0 = 1.0f - x6[l].f;
+                x6[l].f = sqrtf(x6[l].f);
+                a0 = sqrtf(a0);
+                x1[l].f = FLD(c, NRM + 0)[l].f * a0;
+                x2[l].f = FLD(c, NRM + 1)[l].f * a0;
+                x3[l].f = FLD(c, NRM + 2)[l].f * a0;
+            }
+            get_random(r, c, x0);
+            for (int l = 0; l < n; l++)
+            {
+                const float pi = (float)3.14159265358979323846;     /* mat_GPC10, object.cpp:4130 */
+                float a0 = x0[l].f + x0[l].f;
+                a0 = a0 * pi;
+                a0 = a0 - pi;
+                float a4 = cos_ps(a0);
+                a4 = a4 * x6[l].f;
+                x1[l].f = x1[l].f + FLD(c, TEX_U)[l].f * a4;
+                x2[l].f = x2[l].f + FLD(c, TEX_V)[l].f * a4;
+                x3[l].f = x3[l].f + FLD(c, C_PTR)[l].f * a4;
+                a4 = sin_ps(a0);
+                a4 = a4 * x6[l].f;
+                x1[l].f = x1[l].f + FLD(c, C_ACC)[l].f * a4;
+                x2[l].f = x2[l].f + FLD(c, F_RFL)[l].f * a4;
+                x3[l].f = x3[l].f + FLD(c, T_VAL)[l].f * a4;
+                FLD(c, NEW + 0)[l] = x1[l];
+                FLD(c, NEW + 1)[l] = x2[l];
+                FLD(c, NEW + 2)[l] = x3[l];
+                FLD(c, T_NEW)[l].u = 0;
+                x1[l].u = x2[l].u = x3[l].u = 0;
+            }
+            if (r->depth != 0)
+            {
+                /* 2599-2660: the bounce, one level down (PT_ret is tag 4) */
+                const int cc = c + STEP;
+                lvl_t *C = &r->lv[lvl + 1];
+                r->depth -= 1;
+                C->p_flg = L->l_flg | QR_FLAG_PASS_BACK;
+                C->p_lst = s->mat[side];
+                C->p_obj = si;
+                for (int l = 0; l < n; l++)
+                {
+                    FLD(cc, WMASK)[l] = FLD(c, TMASK)[l];
+                    FLD(cc, T_BUF)[l].f = r->h->cam_t_max;
+                    FLD(cc, C_BUF)[l].u = 0;
+                    FLD(cc, COL + 0)[l].u = 0;
+                    FLD(cc, COL + 1)[l].u = 0;
+                    FLD(cc, COL + 2)[l].u = 0;
+                    FLD(cc, T_MIN)[l].u = 0;
+                    if (FLD(c, TMASK)[l].u) r->st.rays_reflect++;
+                }
+                C->l_flg = 0; C->l_lst = NIL; C->l_obj = NIL;
+                walk(r, lvl + 1, s->lst_srf[side]);
+                r->depth += 1;
+                for (int l = 0; l < n; l++)
+                {
+                    x1[l].f = FLD(cc, COL + 0)[l].f * m->l_dff;
+                    x2[l].f = FLD(cc, COL + 1)[l].f * m->l_dff;
+                    x3[l].f = FLD(cc, COL + 2)[l].f * m->l_dff;
+                    x1[l].f = x1[l].f * FLD(c, TEX + 0)[l].f;
+                    x2[l].f = x2[l].f * FLD(c, TEX + 1)[l].f;
+                    x3[l].f = x3[l].f * FLD(c, TEX + 2)[l].f;
+                }
+            }
+        }
+        /* PT_mix 2664-2699: self-emission, then the radiance of the hit lanes */
+        for (int l = 0; l < n; l++)
+        {
+            x1[l].f = x1[l].f + m->col[0];
+            x2[l].f = x2[l].f + m->col[1];
+            x3[l].f = x3[l].f + m->col[2];
+            FLD(c, TMASK)[l] = FLD(c, F_RND)[l];
+            if (FLD(c, TMASK)[l].u == 0) continue;
+            FLD(c, COL + 0)[l] = x1[l];
+            FLD(c, COL + 1)[l] = x2[l];
+            FLD(c, COL + 2)[l] = x3[l];
+        }
+    }
+    else
     if (props & QR_PROP_LIGHT)
     {
         /* LT_set 3164-3177 */
@@ -957,6 +1158,37 @@ static int material(R *r, int lvl, int ei, int kind)
                     a0 = u2f(u0);
                     FLD(c, C_TRN)[l].f = m->c_trn - a0;
                     FLD(c, C_RFL)[l].f = m->c_rfl + a0;
+                }
+                if (r->pt != NULL && !(r->depth > QR_STACK_DEPTH - 2))
+                {
+                    /* 3428-3466 (RT_FEAT_PT_SPLIT_FRESNEL): below the first two
+                     * levels follow ONE of the two rays, chosen with probability
+                     * 0.25 + 0.5 * reflectance share, and weigh it up */
+                    W x0r[MAXS];
+                    get_random(r, c, x0r);
+                    for (int l = 0; l < n; l++)
+                    {
+                        const float a4 = FLD(c, C_TRN)[l].f;
+                        float a5 = FLD(c, C_RFL)[l].f;
+                        float a6 = a5;
+                        float a7 = a4 + a5;
+                        a5 = a5 / a7;
+                        a7 = 0.5f;
+                        a5 = a5 * a7;
+                        a7 = a7 * a7;
+                        a7 = a7 + a5;
+                        const float rn = x0r[l].f;
+                        const uint32_t mt = m_ge(rn, a7) & FLD(c, M_TRN)[l].u;
+                        FLD(c, M_TRN)[l].u = mt;
+                        const uint32_t mr = m_lt(rn, a7) & FLD(c, M_RFL)[l].u;
+                        FLD(c, M_RFL)[l].u = mr;
+                        a5 = a4;
+                        const float a2 = 1.0f - a7;
+                        a5 = a5 / a2;
+                        a6 = a6 / a7;
+                        FLD(c, C_TRN)[l].u = f2u(a5) & mt;
+                        FLD(c, C_RFL)[l].u = f2u(a6) & mr;
+                    }
                 }
             }
 
@@ -1636,9 +1868,39 @@ static void walk(R *r, int lvl, int ei)
 
 /* ---- frame loops: YY_cyc / XX_cyc 1142-1322, epilogue XX_end 5161-5343 ---- */
 
+static int render(const void *blob, size_t bytes, uint32_t *frame,
+                  int stride, int packet, float *t_out,
+                  int y0, int y1, qr_oracle_stats *stats, qr_oracle_pt *pt);
+
+/* rt_Scene::reset_pseed, engine.cpp:3651-3685 (RT_PRNG != LCG48: a 48-bit LCG
+ * seeds the plane, low 32 bits kept) */
+void qr_oracle_pt_seed(uint32_t *pseed, size_t n)
+{
+    uint64_t seed = 1;
+    for (size_t k = 0; k < n; k++)
+    {
+        seed = (seed * 25214903917ull + 11ull) & 0x0000FFFFFFFFFFFFull;
+        pseed[k] = (uint32_t)seed;
+    }
+}
+
 int qr_oracle_render(const void *blob, size_t bytes, uint32_t *frame,
                      int stride, int packet, float *t_out,
                      int y0, int y1, qr_oracle_stats *stats)
+{
+    return render(blob, bytes, frame, stride, packet, t_out, y0, y1, stats, NULL);
+}
+
+int qr_oracle_render_pt(const void *blob, size_t bytes, uint32_t *frame,
+                        int stride, int packet, int y0, int y1, qr_oracle_pt *pt)
+{
+    if (pt == NULL || pt->pseed == NULL || pt->ptr_r == NULL || pt->ptr_g == NULL || pt->ptr_b == NULL) return -6;
+    return render(blob, bytes, frame, stride, packet, NULL, y0, y1, NULL, pt);
+}
+
+static int render(const void *blob, size_t bytes, uint32_t *frame,
+                  int stride, int packet, float *t_out,
+                  int y0, int y1, qr_oracle_stats *stats, qr_oracle_pt *pt)
 {
     const qr_blob_header *h = (const qr_blob_header *)blob;
     if (bytes < sizeof(*h) || h->magic != QR_BLOB_MAGIC) return -1;
@@ -1667,11 +1929,23 @@ int qr_oracle_render(const void *blob, size_t bytes, uint32_t *frame,
     if (y0 < 0) y0 = 0;
     if (y1 > h->y_res) y1 = h->y_res;
 
+    r->pt = pt;
+    if (pt != NULL)
+    {
+        /* 1112-1124: one more sample per pixel sample; its weight, the rest's */
+        pt->pts_c = pt->pts_c + 1.0f;
+        r->pts_o = 1.0f / pt->pts_c;
+        r->pts_u = 1.0f - r->pts_o;
+    }
+
     for (int y = y0; y < y1; y++)
     {
         for (int x = 0; x < h->x_res; x += gpix)
         {
             float colr[MAXS], colg[MAXS], colb[MAXS], tb[MAXS];
+            /* 1168-1174, 5182: the packet's slots in the seed / colour planes,
+             * (y * x_row + x) << fsaa + lane */
+            const size_t slot0 = ((size_t)y * (size_t)h->x_row + (size_t)x) << fsaa;
 
             for (int g0 = 0; g0 < G; g0 += packet)
             {
@@ -1684,17 +1958,55 @@ int qr_oracle_render(const void *blob, size_t bytes, uint32_t *frame,
                 L->l_flg = 0; L->l_lst = NIL; L->l_obj = NIL;
 
                 int px0 = 0;
+                W jx[MAXS], jy[MAXS];
+                for (int l = 0; l < n; l++) jx[l].u = jy[l].u = 0;
+                if (pt != NULL)
+                {
+                    /* 1218-1285 (RT_FEAT_PT_RANDOM_SAMPLE): tent-filtered jitter
+                     * of the sample position, all lanes draw */
+                    r->prngs = slot0 + (size_t)g0;
+                    for (int l = 0; l < n; l++) FLD(0, TMASK)[l].u = ONES;
+                    for (int pass = 0; pass < 2; pass++)
+                    {
+                        W x0[MAXS];
+                        get_random(r, 0, x0);
+                        for (int l = 0; l < n; l++)
+                        {
+                            float a0 = x0[l].f + x0[l].f;
+                            const float a2 = a0;
+                            const uint32_t lt = m_lt(a0, 1.0f);
+                            float a3 = sqrtf(a2);
+                            a3 = a3 - 1.0f;
+                            float a5 = 2.0f - a2;
+                            a5 = sqrtf(a5);
+                            const float b2 = 1.0f - a5;
+                            const uint32_t u = (f2u(a3) & lt) | (~lt & f2u(b2));
+                            (pass == 0 ? jx : jy)[l].u = u;
+                        }
+                    }
+                    for (int l = 0; l < n; l++)
+                    {
+                        jx[l].f = jx[l].f * 0.5f;
+                        jy[l].f = jy[l].f * 0.5f;
+                        if (fsaa != 0)
+                        {
+                            jx[l].f = jx[l].f * 0.5f;
+                            jy[l].f = jy[l].f * 0.5f;
+                        }
+                    }
+                }
                 for (int l = 0; l < n; l++)
                 {
                     const int gl = g0 + l;          /* lane within the group */
                     const int px = x + (gl >> 2) * (4 >> fsaa) + lane_px[fsaa][gl & 3];
                     if (l == 0) px0 = px;
                     /* 1287-1322: ray init; hor_i/ver_i are exact integers
-                     * (engine.cpp:3613-3624), the PT jitter terms are zero */
+                     * (engine.cpp:3613-3624), the PT jitter terms are zero
+                     * unless the path tracer is on */
                     float hs = (float)px + h->hor_a[gl & 3];
                     float vs = (float)y + h->ver_a[gl & 3];
-                    hs = hs + 0.0f;
-                    vs = vs + 0.0f;
+                    hs = hs + jx[l].f;
+                    vs = vs + jy[l].f;
                     for (int k = 0; k < 3; k++)
                     {
                         float a = h->hor[k] * hs;
@@ -1723,6 +2035,24 @@ int qr_oracle_render(const void *blob, size_t bytes, uint32_t *frame,
                     colg[g0 + l] = FLD(0, COL + 1)[l].f;
                     colb[g0 + l] = FLD(0, COL + 2)[l].f;
                     tb[g0 + l]   = FLD(0, T_BUF)[l].f;
+                }
+            }
+
+            if (pt != NULL)
+            {
+                /* 5176-5219: running mean over the frames since set_pton */
+                float *acc[3] = { pt->ptr_r, pt->ptr_g, pt->ptr_b };
+                float *col[3] = { colr, colg, colb };
+                for (int k = 0; k < 3; k++)
+                {
+                    for (int l = 0; l < G; l++)
+                    {
+                        float a0 = col[k][l] * r->pts_o;
+                        const float a1 = acc[k][slot0 + (size_t)l] * r->pts_u;
+                        a0 = a0 + a1;
+                        acc[k][slot0 + (size_t)l] = a0;
+                        col[k][l] = a0;
+                    }
                 }
             }
 

@@ -48,6 +48,31 @@ int qr_oracle_render(const void *blob, size_t bytes, uint32_t *frame,
                      int stride, int packet, float *t_out,
                      int y0, int y1, qr_oracle_stats *stats);
 
+/*
+ * Path-tracer state of a scene (rt_Scene::pseed, ptr_r/g/b, engine.cpp:
+ * 2875-2901; rt_SIMD_INFOX::pts_c): 4 * x_row * y_res entries per plane, slot
+ * ((y * x_row + x) << fsaa) + sample.  reset = rt_Scene::reset_pseed /
+ * reset_color (engine.cpp:3670-3700) and pts_c = 0.
+ */
+typedef struct qr_oracle_pt
+{
+    uint32_t *pseed;
+    float    *ptr_r, *ptr_g, *ptr_b;
+    float     pts_c;
+} qr_oracle_pt;
+
+/* the seed plane as rt_Scene::reset_pseed fills it */
+void qr_oracle_pt_seed(uint32_t *pseed, size_t n);
+
+/*
+ * One more frame of the path tracer (rt_Scene::set_pton(1), render0 with
+ * pt_on, tracer.cpp:1112-1136, 1218-1285, 2339-2701, 3428-3466, 5176-5219).
+ * With packet = S the result is the reference's of that SIMD width; PT results
+ * depend on the width (unmasked side effects of packet-wide branches).
+ */
+int qr_oracle_render_pt(const void *blob, size_t bytes, uint32_t *frame,
+                        int stride, int packet, int y0, int y1, qr_oracle_pt *pt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,9 +120,29 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     if (rows < 0 || rows > (int)s_inf->frm_h) rows = (int)s_inf->frm_h;
 
     qr_oracle_stats st;
-    int rc = qr_oracle_render(blob, bytes, (uint32_t *)s_inf->frame,
+    memset(&st, 0, sizeof(st));
+    int rc;
+    if (s_inf->pt_on != 0)
+    {
+        /* path tracer: the scene's own seed / colour planes, the sample count
+         * where render0 keeps it (tracer.cpp:1112-1136) */
+        qr_oracle_pt pt;
+        pt.pseed = (uint32_t *)s_inf->pseed;
+        pt.ptr_r = (float *)s_inf->ptr_r;
+        pt.ptr_g = (float *)s_inf->ptr_g;
+        pt.ptr_b = (float *)s_inf->ptr_b;
+        pt.pts_c = s_inf->pts_c[0];
+        rc = qr_oracle_render_pt(blob, bytes, (uint32_t *)s_inf->frame,
+                                 (int)s_inf->frm_row, packet, 0, rows, &pt);
+        RT_SIMD_SET(s_inf->pts_c, pt.pts_c);
+    }
+    else
+    {
+        RT_SIMD_SET(s_inf->pts_c, 0.0f);
+        rc = qr_oracle_render(blob, bytes, (uint32_t *)s_inf->frame,
                               (int)s_inf->frm_row, packet, NULL,
                               0, rows, &st);
+    }
     if (rc != 0)
     {
         throw rt_Exception("qr_oracle_render failed");

@@ -265,14 +265,15 @@ static void usage()
            "  [-b time_begin_ms] [-d time_delta_ms] [-n simd -k size -v type]\n"
            "  [-u (freeze update after 1st frame: RT_OPTS_UPDATE_EXT0)]\n"
            "  [-o out.raw (last frame, x_res*y_res u32)] [-q (quiet)]\n"
-           "  [-T t.raw (oracle/_ref/qr_ref_tdump only: primary hit distance per sample)]\n");
+           "  [-T t.raw (oracle/_ref/qr_ref_tdump only: primary hit distance per sample)]\n"
+           "  [-Q (path tracer, rt_Scene::set_pton: -f frames accumulate, use -d 0)]\n");
 }
 
 int main(int argc, char **argv)
 {
     const char *scene_name = "test01", *out = NULL, *opts_s = "default", *t_out = NULL;
     int x_res = 800, y_res = 480, fsaa = 0, threads = 0, frames = 1, warm = 0;
-    int cam_idx = 0, n_simd = 0, k_size = 0, s_type = 0, quiet = 0;
+    int cam_idx = 0, n_simd = 0, k_size = 0, s_type = 0, quiet = 0, pt_mode = 0;
     int gamma_on = 0, fresnel_on = 0, freeze = 0;
     long t_begin = 0, t_delta = 16;
     qr_synth::Params synth = { 1000, 1, 100.0f, 1, 0 };
@@ -301,6 +302,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-o")) { out = v; i++; }
         else if (!strcmp(a, "-q")) { quiet = 1; }
         else if (!strcmp(a, "-T")) { t_out = v; i++; }
+        else if (!strcmp(a, "-Q")) { pt_mode = 1; }
         else if (!strcmp(a, "-N")) { synth.n = atoi(v); i++; }
         else if (!strcmp(a, "-S")) { synth.seed = (unsigned)atol(v); i++; }
         else if (!strcmp(a, "-E")) { synth.extent = (float)atof(v); i++; }
@@ -368,6 +370,12 @@ int main(int argc, char **argv)
         else if (strcmp(opts_s, "default"))
         {
             scene->set_opts((rt_si32)strtoul(opts_s, NULL, 0));
+        }
+
+        if (pt_mode && !scene->set_pton(1))
+        {
+            fprintf(stderr, "the scene does not allow the path tracer (RT_OPTS_PT)\n");
+            return 2;
         }
 
         std::vector<double> ms;

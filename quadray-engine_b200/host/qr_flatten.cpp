@@ -122,6 +122,7 @@ int32_t qr_Flattener::material(const rt_SIMD_MATERIAL *m)
     r.ext_2 = m->ext_2[0];
     r.clamp = m->clamp[0];
     r.cmask = (uint32_t)m->cmask[0];
+    r.col[0] = m->col_r[0]; r.col[1] = m->col_g[0]; r.col[2] = m->col_b[0];
 
     /* texture: (xmask+1) x (ymask+1) texels of 0x00RRGGBB, power of two
      * (object.cpp:4113-4129); a plain colour is a 1x1 texture */
@@ -319,10 +320,6 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     {
         throw rt_Exception("null-pointer in qr_Flattener::build");
     }
-    if (s_inf->pt_on != 0)
-    {
-        throw rt_Exception("path-tracer mode is not supported by B200 backend");
-    }
 
     elem_idx.clear(); surf_idx.clear(); mat_idx.clear();
     lgt_idx.clear();  tex_idx.clear();
@@ -340,6 +337,7 @@ const uint8_t *qr_Flattener::build(const rt_SIMD_INFOX *s_inf, size_t *bytes)
     memset(&h, 0, sizeof(h));
     h.magic   = QR_BLOB_MAGIC;
     h.version = QR_BLOB_VERSION;
+    h.flags   = s_inf->pt_on != 0 ? QR_BLOB_PT : 0u;
 
     h.x_res   = (int32_t)s_inf->frm_w;
     h.y_res   = (int32_t)s_inf->frm_h;
