@@ -13,6 +13,7 @@
 unsigned long long qr_ops[4] = {0, 0, 0, 0};
 #include "qr_core.cuh"
 #include "qr_tiling.cuh"
+#include "qr_pt.cuh"
 
 /* device-tiling emulation: tiles built / elements written since the last call */
 static uint64_t qr_tiling_tiles = 0, qr_tiling_elems = 0;
@@ -159,6 +160,64 @@ extern "C" int qr_hostsim_render(const void *blob, size_t bytes, uint32_t *frame
     {
         rays[0] = primary;
         for (int k = 1; k < 4; k++) rays[k] = qr_sc_ld1(sc, QR_SC_MISC, (uint32_t)k);
+    }
+    return 0;
+}
+
+/*
+ * Path tracer (csrc/qr_pt.cuh) with a "warp" of one lane: one more frame into
+ * the caller's seed / colour planes.  Lanes are grouped in fours for the
+ * anti-aliasing reduce exactly as above.
+ */
+extern "C" int qr_hostsim_render_pt(const void *blob, size_t bytes, uint32_t *frame, int stride,
+                                    int y0, int y1, uint32_t *pseed, float *ptr_r, float *ptr_g,
+                                    float *ptr_b, float *pts_c)
+{
+    const qr_blob_header *h = (const qr_blob_header *)blob;
+    if (bytes < sizeof(*h) || h->magic != QR_BLOB_MAGIC) return -1;
+    if (h->version != QR_BLOB_VERSION || h->total_bytes > bytes) return -2;
+    static qr_pt::R r;
+    qr_pt::init(&r, blob);
+
+    *pts_c = *pts_c + 1.0f;
+    const float pts_o = 1.0f / *pts_c;
+    const float pts_u = 1.0f - pts_o;
+
+    const int fsaa = h->fsaa;
+    static const int lane_px[3][4] = { {0, 1, 2, 3}, {0, 0, 1, 1}, {0, 0, 0, 0} };
+    if (y0 < 0) y0 = 0;
+    if (y1 > h->y_res) y1 = h->y_res;
+    for (int y = y0; y < y1; y++)
+    {
+        for (int x = 0; x < h->x_res; x += 4 >> fsaa)
+        {
+            float c[3][4];
+            const size_t slot0 = ((size_t)y * (size_t)h->x_row + (size_t)x) << fsaa;
+            for (int l = 0; l < 4; l++)
+            {
+                const int px = x + lane_px[fsaa][l];
+                float col[3];
+                qr_pt::trace_lane(&r, y, px, l, px, pseed, ptr_r, ptr_g, ptr_b, slot0 + (size_t)l, pts_o, pts_u, col);
+                for (int k = 0; k < 3; k++) c[k][l] = qr_clamp1(col[k]);
+            }
+            int n = 4;
+            for (int p = 0; p < fsaa; p++)
+            {
+                for (int k = 0; k < 3; k++)
+                {
+                    for (int l = 0; l < n; l++) c[k][l] = qr_mul(c[k][l], 0.5f);
+                    for (int l = 0; l < n / 2; l++) c[k][l] = qr_add(c[k][2 * l], c[k][2 * l + 1]);
+                }
+                n >>= 1;
+            }
+            for (int l = 0; l < (4 >> fsaa); l++)
+            {
+                if (x + l < h->x_res && frame != NULL)
+                {
+                    frame[(size_t)y * stride + x + l] = qr_pack(*h, c[0][l], c[1][l], c[2][l]);
+                }
+            }
+        }
     }
     return 0;
 }
