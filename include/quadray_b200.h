@@ -233,6 +233,30 @@ typedef struct qr_kernel_info
 int qr_kernel_query(qr_ctx *ctx, qr_kernel_info *info);
 
 /*
+ * Path tracer (rt_Scene::set_pton, render0 with pt_on:
+ * core/tracer/tracer.cpp:1112-1136, 1218-1285, 2339-2701, 3428-3466,
+ * 5176-5219).  A blob whose header carries QR_BLOB_PT (the flattener sets it
+ * from rt_SIMD_INFOX::pt_on) is rendered by the packet tracer of csrc/qr_pt.cuh
+ * -- one warp = one 32-lane packet of the reference's 512x2v2 target, frames
+ * bit-identical to that target's -- through the same render calls (not the
+ * pipelined ones, not qr_dump_hits); x_row must be a multiple of 32 >> fsaa.
+ * Every frame adds one sample per pixel sample to a running mean.
+ *
+ * qr_pt_reset   = rt_Scene::reset_pseed + reset_color + inf_PTS_C = 0
+ *                 (engine.cpp:3670-3700): "pseed" is the scene's seed plane of
+ *                 n_slots = 4 * x_row * y_res words (NULL: filled here as
+ *                 reset_pseed fills it), the colour planes start at zero.
+ *                 The state lives on the device(s) from then on.
+ * qr_pt_frames  frames accumulated since the reset.
+ * qr_pt_fetch   copies GPU 0's seed / colour planes out (any pointer may be
+ *                 NULL); for tests and for a caller that wants rt_Scene's host
+ *                 planes current.
+ */
+int qr_pt_reset(qr_ctx *ctx, const uint32_t *pseed, size_t n_slots);
+int qr_pt_frames(qr_ctx *ctx);
+int qr_pt_fetch(qr_ctx *ctx, uint32_t *pseed, float *ptr_r, float *ptr_g, float *ptr_b, size_t n_slots);
+
+/*
  * The checked build of the library (make checked: -DQR_CHECKED,
  * lib/libquadray_b200_checked.so) counts out-of-range element cursors, surface
  * offsets, tile indices, pixel stores, stack levels and scratch reads that

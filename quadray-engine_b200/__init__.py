@@ -30,6 +30,7 @@ SYMBOLS = (
     "qr_kernel_query", "qr_fp32_peak", "qr_pipeline", "qr_render_begin", "qr_render_fetch", "qr_render_end",
     "qr_frame_notify_slot", "qr_render_rows_notify", "qr_wait_notify", "qr_host_register", "qr_host_unregister",
     "qr_check_counters",
+    "qr_pt_reset", "qr_pt_frames", "qr_pt_fetch",
 )
 
 
@@ -75,6 +76,12 @@ def load_library():
     lib.qr_render_rows.restype = ci
     lib.qr_check_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     lib.qr_check_counters.restype = ci
+    lib.qr_pt_reset.argtypes = [vp, vp, ctypes.c_size_t]
+    lib.qr_pt_reset.restype = ci
+    lib.qr_pt_frames.argtypes = [vp]
+    lib.qr_pt_frames.restype = ci
+    lib.qr_pt_fetch.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t]
+    lib.qr_pt_fetch.restype = ci
     lib.qr_host_register.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     lib.qr_host_register.restype = ci
     lib.qr_host_unregister.argtypes = [vp, vp]
@@ -228,6 +235,25 @@ class Context(object):
         full-frame geometry (possibly another GPU's, see frame_ipc_open)."""
         self._check(self.lib.qr_render_rows(self.h, ctypes.c_void_p(dev_ptr), int(stride),
                                             int(tile_row0), int(tile_row_step)))
+
+    def pt_reset(self, n_slots, pseed=None):
+        """Path tracer: new seed plane (the reference's own when pseed is None),
+        colour planes and frame count at zero (rt_Scene::set_pton(1))."""
+        if pseed is not None:
+            pseed = np.ascontiguousarray(pseed, dtype=np.uint32)
+            assert pseed.size == int(n_slots)
+        self._check(self.lib.qr_pt_reset(self.h, pseed.ctypes.data if pseed is not None else None, int(n_slots)))
+
+    def pt_frames(self):
+        return int(self.lib.qr_pt_frames(self.h))
+
+    def pt_fetch(self, n_slots):
+        """(seeds, red, green, blue) planes of GPU 0."""
+        sd = np.empty(int(n_slots), dtype=np.uint32)
+        pl = [np.empty(int(n_slots), dtype=np.float32) for _ in range(3)]
+        self._check(self.lib.qr_pt_fetch(self.h, sd.ctypes.data, pl[0].ctypes.data, pl[1].ctypes.data,
+                                         pl[2].ctypes.data, int(n_slots)))
+        return sd, pl[0], pl[1], pl[2]
 
     def check_counters(self):
         """Violation counters of the checked build (raises in the normal build)."""

@@ -35,6 +35,7 @@
 #include "quadray_b200.h"
 #include "qr_core.cuh"
 #include "qr_tiling.cuh"
+#include "qr_pt.cuh"
 
 /*
  * Launch shapes (threads per CTA, resident CTAs per SM the register budget is
@@ -363,6 +364,84 @@ qr_render_kernel(const qr_launch p)
 }
 
 /*
+ * Path tracer (qr_pt.cuh): one warp = one packet of the reference's 512x2v2
+ * target, 32 >> fsaa pixels of one row; the warps of a persistent grid draw
+ * packets from a counter.  Every lane of a packet is traced, also those right
+ * of x_res (the reference traces them: they vote in the packet-wide tests).
+ */
+struct qr_pt_launch
+{
+    const uint8_t *blob;        /* the scene blob as flattened (not the kscene image) */
+    uint32_t      *frame;
+    int            stride;
+    int            ty0, ty_step, n_trows;
+    uint32_t      *pseed;       /* seed and colour planes, slot ((y * x_row + x) << fsaa) + lane */
+    float         *ptr_r, *ptr_g, *ptr_b;
+    float          pts_o, pts_u;/* 1 / frames so far, 1 - that */
+    unsigned int  *queue;       /* zero at launch */
+};
+
+#define QR_PT_THREADS 128
+#define QR_PT_STACK   (16 * 1024)   /* bytes per thread: 13 contexts deep walk -> material -> walk recursion */
+
+__global__ void __launch_bounds__(QR_PT_THREADS)
+qr_pt_kernel(const qr_pt_launch p)
+{
+    qr_pt::R r;
+    qr_pt::init(&r, p.blob);
+    const qr_blob_header &h = *r.h;
+    const int lane = threadIdx.x & 31;
+    const int fsaa = h.fsaa;
+    const int ppp = 32 >> fsaa;                             /* pixels per packet */
+    const unsigned int per_row = (unsigned int)((h.x_res + ppp - 1) / ppp);
+    const unsigned int n_items = (unsigned int)p.n_trows * (unsigned int)h.tile_h * per_row;
+    const int lpx = (lane >> 2) * (4 >> fsaa) + (fsaa == 0 ? (lane & 3) : fsaa == 1 ? ((lane & 3) >> 1) : 0);
+
+    for (;;)
+    {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(p.queue, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_items) break;
+        const unsigned int rw = item / per_row;
+        const int x = (int)(item % per_row) * ppp;
+        const int y = (p.ty0 + (int)(rw / (unsigned int)h.tile_h) * p.ty_step) * h.tile_h
+                    + (int)(rw % (unsigned int)h.tile_h);
+        if (y >= h.y_res) continue;
+
+        float col[3];
+        const size_t slot = (((size_t)y * (size_t)h.x_row + (size_t)x) << fsaa) + (size_t)lane;
+        qr_pt::trace_lane(&r, y, x + lpx, lane, x, p.pseed, p.ptr_r, p.ptr_g, p.ptr_b, slot,
+                          p.pts_o, p.pts_u, col);
+        __syncwarp();
+
+        /* XX_end 5221-5343 as in qr_render_kernel */
+        float cr = qr_clamp1(col[0]), cg = qr_clamp1(col[1]), cb = qr_clamp1(col[2]);
+        for (int pass = 0; pass < fsaa; pass++)
+        {
+            const int d = 1 << pass;
+            cr = qr_mul(cr, 0.5f); cg = qr_mul(cg, 0.5f); cb = qr_mul(cb, 0.5f);
+            const float r2 = __shfl_xor_sync(0xFFFFFFFFu, cr, d);
+            const float g2 = __shfl_xor_sync(0xFFFFFFFFu, cg, d);
+            const float b2 = __shfl_xor_sync(0xFFFFFFFFu, cb, d);
+            if ((lane & d) == 0)
+            {
+                cr = qr_add(cr, r2); cg = qr_add(cg, g2); cb = qr_add(cb, b2);
+            }
+            else
+            {
+                cr = qr_add(r2, cr); cg = qr_add(g2, cg); cb = qr_add(b2, cb);
+            }
+        }
+        const int pxo = x + (lane >> fsaa);
+        if ((lane & ((1 << fsaa) - 1)) == 0 && pxo < h.x_res)
+        {
+            p.frame[(size_t)y * p.stride + pxo] = qr_pack(h, cr, cg, cb);
+        }
+    }
+}
+
+/*
  * Device-side tiling (qr_tiling.cuh), two launches per uploaded scene: the
  * tile rectangle of every leaf of the camera list, then one list per tile.
  */
@@ -478,6 +557,10 @@ struct qr_dev
     unsigned int   *queue_d;                        /* [0] work-item counter, [1] finished warps */
     unsigned int    queue_base;                     /* where the counter stands (see qr_launch) */
     unsigned long long *rays_d;
+    /* path tracer: the blob as flattened, the seed and colour planes of the frame */
+    uint8_t        *raw_d;      size_t raw_cap;
+    uint32_t       *pt_seed;    float *pt_col[3];   size_t pt_slots;
+    bool            pt_stack;   /* the stack limit of the recursive packet tracer is set */
     int             sm_count;
     int             ctas_per_sm;
     int             smem_optin;
@@ -500,6 +583,9 @@ struct qr_ctx
     qr_dev          dev[QR_MAX_DEV];
     qr_blob_header  hdr;
     bool            have_scene;
+    bool            pt_scene;       /* the scene asks for the path tracer (QR_BLOB_PT) */
+    float           pt_count;       /* frames accumulated since qr_pt_reset (inf_PTS_C) */
+    float           pt_o, pt_u;     /* 1 / pt_count and 1 - that, for the frame in progress */
     uint32_t        stage_bytes;
     uint64_t        launches;
     uint64_t        rays[4];
@@ -749,6 +835,8 @@ extern "C" void qr_shutdown(qr_ctx *ctx)
         if (d.frame_h) cudaFreeHost(d.frame_h);
         if (d.t_d)     cudaFree(d.t_d);
         if (d.queue_d) cudaFree(d.queue_d);
+        if (d.raw_d) cudaFree(d.raw_d);
+        if (d.pt_seed) cudaFree(d.pt_seed);
         if (d.rays_d)  cudaFree(d.rays_d);
     }
     delete ctx;
@@ -983,7 +1071,183 @@ extern "C" int qr_scene_upload(qr_ctx *ctx, const void *blob, size_t bytes)
         }
         d.ctas_per_sm = nb;
     }
+    ctx->pt_scene = (h->flags & QR_BLOB_PT) != 0;
+    if (ctx->pt_scene)
+    {
+        /* the packet tracer reads the blob as it is; its seed and colour planes
+         * are laid out for packets of 32 >> fsaa pixels (qr_pt.cuh) */
+        if (ctx->pipelined || (h->x_row % (32 >> h->fsaa)) != 0 || h->x_row < h->x_res)
+        {
+            return qr_fail(ctx, QR_E_STATE, "path-traced scene: needs x_row %% %d == 0 and no pipelined mode",
+                           32 >> h->fsaa);
+        }
+        for (int i = 0; i < ctx->ndev; i++)
+        {
+            qr_dev &d = ctx->dev[i];
+            QR_CUDA(ctx, cudaSetDevice(d.id));
+            rc = qr_grow(ctx, (void **)&d.raw_d, &d.raw_cap, h->total_bytes, false);
+            if (rc != QR_OK)
+            {
+                return rc;
+            }
+            QR_CUDA(ctx, cudaMemcpyAsync(d.raw_d, blob, h->total_bytes, cudaMemcpyHostToDevice, d.stream));
+        }
+    }
     ctx->have_scene = true;
+    return QR_OK;
+}
+
+extern "C" int qr_pt_reset(qr_ctx *ctx, const uint32_t *pseed, size_t n_slots)
+{
+    if (ctx == NULL || n_slots == 0)
+    {
+        return QR_E_ARG;
+    }
+    uint32_t *gen = NULL;
+    if (pseed == NULL)
+    {
+        /* rt_Scene::reset_pseed, engine.cpp:3651-3685: a 48-bit LCG fills the plane */
+        gen = (uint32_t *)malloc(n_slots * sizeof(uint32_t));
+        if (gen == NULL)
+        {
+            return qr_fail(ctx, QR_E_CUDA, "qr_pt_reset: out of host memory");
+        }
+        unsigned long long seed = 1;
+        for (size_t k = 0; k < n_slots; k++)
+        {
+            seed = (seed * 25214903917ull + 11ull) & 0x0000FFFFFFFFFFFFull;
+            gen[k] = (uint32_t)seed;
+        }
+        pseed = gen;
+    }
+    int rc = QR_OK;
+    for (int i = 0; i < ctx->ndev && rc == QR_OK; i++)
+    {
+        qr_dev &d = ctx->dev[i];
+        cudaError_t e = cudaSetDevice(d.id);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        if (e == cudaSuccess && d.pt_slots != n_slots)
+        {
+            if (d.pt_seed != NULL) cudaFree(d.pt_seed);
+            d.pt_seed = NULL;
+            d.pt_slots = 0;
+            /* one block: seeds, then the three colour planes */
+            e = cudaMalloc((void **)&d.pt_seed, n_slots * 4 * sizeof(uint32_t));
+            if (e == cudaSuccess)
+            {
+                d.pt_slots = n_slots;
+                for (int k = 0; k < 3; k++) d.pt_col[k] = (float *)(d.pt_seed + (size_t)(k + 1) * n_slots);
+            }
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d.pt_seed, pseed, n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d.pt_col[0], 0, n_slots * 3 * sizeof(float), d.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess)
+        {
+            rc = qr_fail(ctx, QR_E_CUDA, "qr_pt_reset: %s", cudaGetErrorString(e));
+        }
+    }
+    free(gen);
+    ctx->pt_count = 0.0f;
+    return rc;
+}
+
+extern "C" int qr_pt_frames(qr_ctx *ctx)
+{
+    return ctx == NULL ? 0 : (int)ctx->pt_count;
+}
+
+extern "C" int qr_pt_fetch(qr_ctx *ctx, uint32_t *pseed, float *ptr_r, float *ptr_g, float *ptr_b, size_t n_slots)
+{
+    if (ctx == NULL)
+    {
+        return QR_E_ARG;
+    }
+    qr_dev &d = ctx->dev[0];
+    if (d.pt_seed == NULL || n_slots > d.pt_slots)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_pt_fetch: no path-tracer state of that size");
+    }
+    QR_CUDA(ctx, cudaSetDevice(d.id));
+    QR_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    float *dst[3] = { ptr_r, ptr_g, ptr_b };
+    if (pseed != NULL) QR_CUDA(ctx, cudaMemcpy(pseed, d.pt_seed, n_slots * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++)
+    {
+        if (dst[k] != NULL) QR_CUDA(ctx, cudaMemcpy(dst[k], d.pt_col[k], n_slots * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return QR_OK;
+}
+
+/* a path-traced frame begins: one more sample per pixel sample (tracer.cpp:1112-1124) */
+static int qr_pt_frame(qr_ctx *ctx, const char *who)
+{
+    if (!ctx->pt_scene)
+    {
+        return QR_OK;
+    }
+    const qr_blob_header &h = ctx->hdr;
+    const size_t need = ((size_t)h.x_row * (size_t)h.y_res) << h.fsaa;
+    for (int i = 0; i < ctx->ndev; i++)
+    {
+        if (ctx->dev[i].pt_seed == NULL || ctx->dev[i].pt_slots < need)
+        {
+            return qr_fail(ctx, QR_E_STATE, "%s: the scene asks for the path tracer, qr_pt_reset first "
+                           "(%zu slots needed)", who, need);
+        }
+    }
+    ctx->pt_count = ctx->pt_count + 1.0f;
+    ctx->pt_o = 1.0f / ctx->pt_count;
+    ctx->pt_u = 1.0f - ctx->pt_o;
+    return QR_OK;
+}
+
+/* the path tracer's launch of tile rows ty0, ty0 + step, ... on GPU i */
+static int qr_launch_rows_pt(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
+                             int ty0, int step, int n, bool first, unsigned int *notify)
+{
+    qr_dev &d = ctx->dev[i];
+    if (!d.pt_stack)
+    {
+        /* walk -> material -> walk recursion, up to 13 contexts deep */
+        QR_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, QR_PT_STACK));
+        d.pt_stack = true;
+    }
+    qr_pt_launch p;
+    p.blob = d.raw_d;
+    p.frame = frame_dev;
+    p.stride = stride;
+    p.ty0 = ty0;
+    p.ty_step = step;
+    p.n_trows = n;
+    p.pseed = d.pt_seed;
+    p.ptr_r = d.pt_col[0]; p.ptr_g = d.pt_col[1]; p.ptr_b = d.pt_col[2];
+    p.pts_o = ctx->pt_o;
+    p.pts_u = ctx->pt_u;
+    /* the path tracer's own counter: word 1 of the queue block is free while no notify launch runs */
+    p.queue = d.queue_d + 1;
+    QR_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(unsigned int), d.stream));
+    if (first)
+    {
+        QR_CUDA(ctx, cudaEventRecord(d.ev0, d.stream));
+    }
+    const int ppp = 32 >> ctx->hdr.fsaa;
+    const unsigned int packets = (unsigned int)n * (unsigned int)ctx->hdr.tile_h
+                               * (unsigned int)((ctx->hdr.x_res + ppp - 1) / ppp);
+    unsigned int grid = (unsigned int)d.sm_count * 4u;
+    const unsigned int need = (packets + QR_PT_THREADS / 32 - 1) / (QR_PT_THREADS / 32);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    qr_pt_kernel<<<grid, QR_PT_THREADS, 0, d.stream>>>(p);
+    QR_CUDA(ctx, cudaGetLastError());
+    if (notify != NULL)
+    {
+        qr_add_kernel<<<1, 1, 0, d.stream>>>(notify);
+        QR_CUDA(ctx, cudaGetLastError());
+    }
+    QR_CUDA(ctx, cudaEventRecord(d.ev1, d.stream));
+    d.timed = true;
+    ctx->launches++;
     return QR_OK;
 }
 
@@ -998,6 +1262,14 @@ static int qr_launch_rows(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride,
     if (n <= 0)
     {
         return QR_OK;
+    }
+    if (ctx->pt_scene)
+    {
+        if (t_out != NULL)
+        {
+            return qr_fail(ctx, QR_E_STATE, "no dump mode for a path-traced scene");
+        }
+        return qr_launch_rows_pt(ctx, i, frame_dev, stride, ty0, step, n, first, notify);
     }
 
     qr_launch p;
@@ -1370,6 +1642,10 @@ extern "C" int qr_render_device(qr_ctx *ctx, uint32_t *frame_dev, int stride, in
     {
         return qr_fail(ctx, QR_E_ARG, "qr_render_device: bad arguments");
     }
+    {
+        const int prc = qr_pt_frame(ctx, "qr_render_device");
+        if (prc != QR_OK) return prc;
+    }
     const int ty0 = y0 / h.tile_h;
     const int ty1 = (y1 + h.tile_h - 1) / h.tile_h;
     for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
@@ -1412,6 +1688,10 @@ extern "C" int qr_render_rows_notify(qr_ctx *ctx, uint32_t *frame_dev, int strid
     }
     const int n = tile_row0 < h.tls_col ? (h.tls_col - tile_row0 + tile_row_step - 1) / tile_row_step : 0;
     for (int i = 1; i < ctx->ndev; i++) ctx->dev[i].timed = false;
+    {
+        const int prc = qr_pt_frame(ctx, "qr_render_rows");
+        if (prc != QR_OK) return prc;
+    }
     int rc = qr_launch_rows(ctx, 0, frame_dev, stride, tile_row0, tile_row_step, n, NULL, true,
                             (unsigned int *)notify_dev);
     if (rc == QR_OK && n <= 0 && notify_dev != NULL)
@@ -1616,6 +1896,10 @@ extern "C" int qr_render(qr_ctx *ctx, uint32_t *frame, int stride)
     if (frame != NULL && (stride < h.x_res && -stride < h.x_res))
     {
         return qr_fail(ctx, QR_E_ARG, "qr_render: stride smaller than x_res");
+    }
+    {
+        const int prc = qr_pt_frame(ctx, "qr_render");
+        if (prc != QR_OK) return prc;
     }
     if (frame == NULL)
     {
@@ -2082,6 +2366,10 @@ extern "C" int qr_dump_hits(qr_ctx *ctx, float *t_out)
     if (!ctx->have_scene)
     {
         return qr_fail(ctx, QR_E_STATE, "qr_dump_hits: no scene uploaded");
+    }
+    if (ctx->pt_scene)
+    {
+        return qr_fail(ctx, QR_E_STATE, "qr_dump_hits: no dump mode for a path-traced scene");
     }
     const qr_blob_header &h = ctx->hdr;
     const size_t n = ((size_t)h.x_res * h.y_res) << h.fsaa;

@@ -232,6 +232,37 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
         }
     }
 
+    /*
+     * Path tracer (rt_Scene::set_pton): the seed and colour planes live on the
+     * device from the first frame on.  rt_Scene resets its host planes when the
+     * mode is switched on (engine.cpp:3731-3741); that shows here as the first
+     * pt_on frame, other planes, or the marker this backend leaves in the host's
+     * red plane (nothing else reads it while the backend renders) wiped by
+     * reset_color.  (Switched off and on again with no frame in between, the
+     * reference keeps counting samples; here the count restarts with the planes.)
+     */
+    static struct { bool on; const void *pseed; size_t slots; } g_pt = { false, RT_NULL, 0 };
+    static const rt_ui32 pt_mark = 0x7FC0B200u;
+    if (s_inf->pt_on != 0)
+    {
+        if (g_pipelined)
+        {
+            throw rt_Exception("B200 backend: no path tracer in pipelined mode (QR_B200_PIPELINE)");
+        }
+        const size_t slots = (size_t)4 * (size_t)s_inf->frm_row * (size_t)s_inf->frm_h;
+        const bool fresh = !g_pt.on || g_pt.pseed != s_inf->pseed || g_pt.slots != slots
+                        || memcmp(s_inf->ptr_r, &pt_mark, sizeof(pt_mark)) != 0;
+        if (fresh && qr_pt_reset(g_ctx, (const uint32_t *)s_inf->pseed, slots) != QR_OK)
+        {
+            qr_throw("B200 path-tracer reset failed", g_ctx);
+        }
+        g_pt.on = true; g_pt.pseed = s_inf->pseed; g_pt.slots = slots;
+    }
+    else
+    {
+        g_pt.on = false;
+    }
+
     if (qr_scene_upload(g_ctx, blob, bytes) != QR_OK)
     {
         qr_throw("B200 scene upload failed", g_ctx);
@@ -296,6 +327,15 @@ rt_void rt_Platform::render0(rt_SIMD_INFOX *s_inf)
     if (qr_render(g_ctx, (uint32_t *)s_inf->frame, (int)s_inf->frm_row) != QR_OK)
     {
         qr_throw("B200 render failed", g_ctx);
+    }
+    if (s_inf->pt_on != 0)
+    {
+        memcpy(s_inf->ptr_r, &pt_mark, sizeof(pt_mark));
+        RT_SIMD_SET(s_inf->pts_c, (rt_real)qr_pt_frames(g_ctx));
+    }
+    else
+    {
+        RT_SIMD_SET(s_inf->pts_c, 0.0f);
     }
     static double t_last = 0.0, sum[6] = { 0, 0, 0, 0, 0, 0 };
     if (timing)

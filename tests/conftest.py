@@ -23,7 +23,10 @@ GOLDEN_CRC = [g for g in _NPZ if g.endswith("c")]
 # "..._T" fixtures hold the reference's own primary hit distances (dump mode),
 # written by the patched scratch build oracle/Makefile `tdump` makes
 GOLDEN_T = [g for g in _NPZ if g.endswith("_T")]
-GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h") and not g.endswith("c") and not g.endswith("_T")]
+# "..._pt" fixtures: path tracer (blob with QR_BLOB_PT, the reference's frame after N accumulated frames)
+GOLDEN_PT = [g for g in _NPZ if g.endswith("_pt")]
+GOLDEN_ALL = [g for g in _NPZ if not g.endswith("h") and not g.endswith("c") and not g.endswith("_T")
+              and not g.endswith("_pt")]
 # the 1080p frame is the bench workload; CPU tests use the 800x480 cases
 GOLDEN_SMALL = [g for g in GOLDEN_ALL if "1080p" not in g]
 

@@ -147,6 +147,45 @@ CASES_T = {
 }
 
 
+# Path tracer ("_pt" suffix): the frame the unmodified reference
+# shows after N accumulated frames of rt_Scene::set_pton(1) at a fixed time
+# (harness -Q -f N -d 0), and the scene blob (QR_BLOB_PT set).  The reference's
+# path-traced frames depend on its SIMD width: these are the 512x2v2 target's.
+CASES_PT = {
+    "test18_a4_pt":    ("-s test18 -x 160 -y 96 -a 2", 3),
+    "test18_a2rg_pt":  ("-s test18 -x 160 -y 96 -a 1 -r -g", 3),
+    "test18_q_pt":     ("-s test18 -x 320 -y 200 -r", 4),
+    "test17_r_pt":     ("-s test17 -x 160 -y 96 -r", 3),       # packet 1 differs here (Fresnel split under mixed TIR)
+    "test02_a2rg_pt":  ("-s test02 -x 160 -y 96 -a 1 -r -g", 3),
+    "test05_odd_pt":   ("-s test05 -x 99 -y 40 -a 2", 2),      # x_res not a multiple of the packet
+    "test16_none_pt":  ("-s test16 -x 48 -y 30 -a 1 -p none", 2),
+    "demo02_rg_pt":    ("-s demo02 -x 96 -y 56 -r -g", 3),
+    "demo03_a4rg_pt":  ("-s demo03 -x 96 -y 56 -a 2 -r -g", 2),
+}
+
+
+def main_pt(names):
+    for name in names:
+        a, frames = CASES_PT[name]
+        args = a.split() + ["-Q", "-d", "0"]
+        with tempfile.TemporaryDirectory() as td:
+            rf, r1, of, bf = (os.path.join(td, n) for n in ("r.raw", "r1.raw", "o.raw", "s.blob"))
+            jr = run([REF] + args + ["-f", str(frames), "-o", rf])
+            run([REF] + args + ["-f", "1", "-o", r1])
+            run([ORC] + args + ["-f", "1", "-o", of], {"QR_DUMP_BLOB": bf, "QR_ORACLE_PACKET": "32"})
+            w, h = jr["x_res"], jr["y_res"]
+            frame = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
+            frame1 = np.fromfile(r1, dtype=np.uint32).reshape(h, w)
+            assert np.array_equal(frame1, np.fromfile(of, dtype=np.uint32).reshape(h, w)), name
+            blob = np.fromfile(bf, dtype=np.uint8)
+        meta = {"name": name, "args": a, "frames": frames, "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
+                "opts": jr["opts"], "ref_simd": jr["simd"], "lit": float((frame != 0).mean())}
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, blob=blob, frame=frame, frame1=frame1,
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+        print("%-20s %4dx%-4d %d frames, lit %.3f  npz %7d B" % (name, w, h, frames, meta["lit"], os.path.getsize(path)))
+
+
 def main_t(names):
     tdump = os.path.join(ROOT, "oracle", "_ref", "qr_ref_tdump")
     for name in names:
@@ -276,8 +315,9 @@ def main(names):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED) + list(CASES_CRC) + list(CASES_T))
+    names = sys.argv[1:] or (list(CASES) + list(CASES_HASHED) + list(CASES_CRC) + list(CASES_T) + list(CASES_PT))
     main([n for n in names if n in CASES])
     main_hashed([n for n in names if n in CASES_HASHED])
     main_crc([n for n in names if n in CASES_CRC])
     main_t([n for n in names if n in CASES_T])
+    main_pt([n for n in names if n in CASES_PT])
