@@ -1211,6 +1211,8 @@ static int qr_launch_rows_pt(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride
     {
         /* walk -> material -> walk recursion, up to 13 contexts deep */
         QR_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, QR_PT_STACK));
+        /* no shared memory in this kernel: all of the SM's array to L1, where the context stacks live */
+        QR_CUDA(ctx, cudaFuncSetAttribute((const void *)qr_pt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
         d.pt_stack = true;
     }
     qr_pt_launch p;
@@ -1234,7 +1236,10 @@ static int qr_launch_rows_pt(qr_ctx *ctx, int i, uint32_t *frame_dev, int stride
     const int ppp = 32 >> ctx->hdr.fsaa;
     const unsigned int packets = (unsigned int)n * (unsigned int)ctx->hdr.tile_h
                                * (unsigned int)((ctx->hdr.x_res + ppp - 1) / ppp);
-    unsigned int grid = (unsigned int)d.sm_count * 4u;
+    /* QR_B200_PT_CTAS=<n>: resident CTAs per SM the grid is sized for (tuning) */
+    static const int pt_ctas = getenv("QR_B200_PT_CTAS") != NULL && atoi(getenv("QR_B200_PT_CTAS")) > 0
+                             ? atoi(getenv("QR_B200_PT_CTAS")) : 8;
+    unsigned int grid = (unsigned int)d.sm_count * (unsigned int)pt_ctas;
     const unsigned int need = (packets + QR_PT_THREADS / 32 - 1) / (QR_PT_THREADS / 32);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
