@@ -182,6 +182,31 @@ def test_gpu_path_tracer_state_is_required_and_resettable(entry, pkg):
     assert np.array_equal(a, z["frame1"]) and np.array_equal(c, z["frame1"])
 
 
+@pytest.mark.gpu
+def test_gpu_path_tracer_on_several_devices(entry, pkg):
+    """One context over several GPUs: every device keeps the seed / colour planes
+    of the tile rows it is dealt.  Needs >= 2 devices."""
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for name in ("test18_q_pt", "test05_odd_pt"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        meta = json.loads(bytes(z["meta"]).decode())
+        b = np.ascontiguousarray(z["blob"], dtype=np.uint8)
+        w, h, row, n = geometry(b)
+        ctx = pkg.Context(list(range(nd)))
+        try:
+            ctx.upload(b)
+            ctx.pt_reset(n)
+            for _ in range(meta["frames"]):
+                ctx.upload(b)
+                fr = ctx.render_frame()
+        finally:
+            ctx.close()
+        assert int((fr != z["frame"]).sum()) == 0, name
+
+
 HARNESS = os.path.join(ROOT, "build", "qr_b200_harness")
 
 
