@@ -384,7 +384,10 @@ struct qr_pt_launch
 #define QR_PT_THREADS 128
 #define QR_PT_STACK   (16 * 1024)   /* bytes per thread: 13 contexts deep walk -> material -> walk recursion */
 
-__global__ void __launch_bounds__(QR_PT_THREADS)
+#ifndef QR_PT_MINBLOCKS
+#define QR_PT_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(QR_PT_THREADS, QR_PT_MINBLOCKS)
 qr_pt_kernel(const qr_pt_launch p)
 {
     qr_pt::R r;
