@@ -11,8 +11,11 @@ import __graft_entry__ as ge  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "test18_q_pt"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
-b = np.ascontiguousarray(z["blob"], dtype=np.uint8)
+if name.endswith(".blob"):
+    b = np.fromfile(name, dtype=np.uint8)
+else:
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    b = np.ascontiguousarray(z["blob"], dtype=np.uint8)
 hdr = b[:256].view(np.int32)
 n = 4 * int(hdr[6]) * int(hdr[5])
 pkg = ge.load_package()
