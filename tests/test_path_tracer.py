@@ -66,19 +66,22 @@ def fresh_state(oracle, n):
 _memo = {}
 
 
-def oracle_frames(oracle, blob, frames, packet):
-    """Frame after 1 and after "frames" frames, and the final state."""
+def oracle_frames(oracle, blob, frames, packet, rows=None):
+    """Frame after 1 and after "frames" frames, and the final state.  "rows":
+    only that band of the frame (packets never leave their row, and a row's
+    seeds and colours are its own, so a band accumulates like the frame)."""
     b = np.ascontiguousarray(blob, dtype=np.uint8)
-    key = (b.tobytes()[:4096], b.size, frames, packet)
+    key = (b.tobytes()[:4096], b.size, frames, packet, rows)
     if key in _memo:
         return _memo[key]
     w, h, row, n = geometry(b)
+    y0, y1 = rows if rows is not None else (0, h)
     sd, pr, pg, pb = fresh_state(oracle, n)
     st = PtState(sd.ctypes.data, pr.ctypes.data, pg.ctypes.data, pb.ctypes.data, 0.0)
     fr = np.zeros((h, w), np.uint32)
     first = None
     for k in range(frames):
-        assert oracle.qr_oracle_render_pt(b.ctypes.data, b.size, fr.ctypes.data, w, packet, 0, h, ctypes.byref(st)) == 0
+        assert oracle.qr_oracle_render_pt(b.ctypes.data, b.size, fr.ctypes.data, w, packet, y0, y1, ctypes.byref(st)) == 0
         if k == 0:
             first = fr.copy()
     assert st.pts_c == float(frames)
@@ -91,9 +94,12 @@ def test_oracle_path_tracer_renders_the_reference_frames(entry, oracle, name):
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     meta = json.loads(bytes(z["meta"]).decode())
     assert int(np.ascontiguousarray(z["blob"][12:16]).view(np.uint32)[0]) & 0x100      # QR_BLOB_PT
-    first, last, _ = oracle_frames(oracle, z["blob"], meta["frames"], 32)
-    assert int((first != z["frame1"]).sum()) == 0
-    assert int((last != z["frame"]).sum()) == 0
+    # a band of the frame here (the CPU suite's time); the GPU tests compare whole frames and states
+    h = meta["y_res"]
+    band = (h // 3, h // 3 + max(8, h // 4))
+    first, last, _ = oracle_frames(oracle, z["blob"], meta["frames"], 32, band)
+    assert int((first[band[0]:band[1]] != z["frame1"][band[0]:band[1]]).sum()) == 0
+    assert int((last[band[0]:band[1]] != z["frame"][band[0]:band[1]]).sum()) == 0
 
 
 def test_path_traced_frames_depend_on_the_packet_width(oracle):
