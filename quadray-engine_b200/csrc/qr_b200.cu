@@ -385,7 +385,7 @@ struct qr_pt_launch
 #define QR_PT_STACK   (16 * 1024)   /* bytes per thread: 13 contexts deep walk -> material -> walk recursion */
 
 #ifndef QR_PT_MINBLOCKS
-#define QR_PT_MINBLOCKS 1
+#define QR_PT_MINBLOCKS 8     /* 64 registers: 32 warps per SM (the measured configuration) */
 #endif
 __global__ void __launch_bounds__(QR_PT_THREADS, QR_PT_MINBLOCKS)
 qr_pt_kernel(const qr_pt_launch p)
