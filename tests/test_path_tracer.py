@@ -102,6 +102,19 @@ def test_oracle_path_tracer_renders_the_reference_frames(entry, oracle, name):
     assert int((last[band[0]:band[1]] != z["frame"][band[0]:band[1]]).sum()) == 0
 
 
+@pytest.mark.parametrize("name,lanes", [("test18_a4_pt", 8), ("test18_a4_pt", 16), ("test02_a2rg_pt", 8),
+                                        ("test02_a2rg_pt", 16), ("test17_r_pt", 16), ("demo02_rg_pt", 8)])
+def test_oracle_follows_the_reference_at_other_simd_widths(oracle, name, lanes):
+    """The reference's 256x1v2 (8 lanes) and 512x1v2 (16 lanes) targets render
+    their own path-traced frames; the oracle at packet = 8 / 16 renders those."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    h = meta["y_res"]
+    band = (h // 3, h // 3 + max(8, h // 4))
+    _, last, _ = oracle_frames(oracle, z["blob"], meta["frames"], lanes, band)
+    assert int((last[band[0]:band[1]] != z["frame_w%d" % lanes][band[0]:band[1]]).sum()) == 0
+
+
 def test_path_traced_frames_depend_on_the_packet_width(oracle):
     """The property that forces a packet tracer on the GPU: with every sample
     deciding alone (packet = 1) a few pixels differ from the 32-lane target's."""

@@ -164,6 +164,9 @@ CASES_PT = {
 }
 
 
+PT_WIDTHS = ("test18_a4_pt", "test02_a2rg_pt", "test17_r_pt", "demo02_rg_pt")
+
+
 def main_pt(names):
     for name in names:
         a, frames = CASES_PT[name]
@@ -178,11 +181,19 @@ def main_pt(names):
             frame1 = np.fromfile(r1, dtype=np.uint32).reshape(h, w)
             assert np.array_equal(frame1, np.fromfile(of, dtype=np.uint32).reshape(h, w)), name
             blob = np.fromfile(bf, dtype=np.uint8)
+            # the same frames from the reference's narrower AVX targets (8 and 16 lanes): the
+            # path tracer's result depends on the SIMD width, the oracle follows it at packet = S
+            extra = {}
+            if name in PT_WIDTHS:
+                for lanes, target in ((8, "-n 256 -k 1 -v 2"), (16, "-n 512 -k 1 -v 2")):
+                    jw = run([REF] + args + target.split() + ["-f", str(frames), "-o", rf])
+                    assert jw["simd"] == {8: "256x1v2", 16: "512x1v2"}[lanes], jw["simd"]
+                    extra["frame_w%d" % lanes] = np.fromfile(rf, dtype=np.uint32).reshape(h, w)
         meta = {"name": name, "args": a, "frames": frames, "x_res": w, "y_res": h, "fsaa": jr["fsaa"],
                 "opts": jr["opts"], "ref_simd": jr["simd"], "lit": float((frame != 0).mean())}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, blob=blob, frame=frame, frame1=frame1,
-                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+                            meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **extra)
         print("%-20s %4dx%-4d %d frames, lit %.3f  npz %7d B" % (name, w, h, frames, meta["lit"], os.path.getsize(path)))
 
 
